@@ -1,0 +1,70 @@
+// decode.cu -- kernel + launcher for the batched decoder (see lz4_decode.cuh for the algorithm).
+#include "kernels.h"
+#include "lz4_decode.cuh"
+
+namespace lz4b200 {
+
+constexpr int DEC_THREADS = 128;
+
+// Persistent CTAs; each group of G lanes pulls the next block index from a global counter.
+template <int G, bool KNOWN>
+__global__ void __launch_bounds__(DEC_THREADS)
+lz4_decode_kernel(BatchArgs a, uint32_t* counter)
+{
+    constexpr int GROUPS = DEC_THREADS / G;
+    __shared__ DecRing rings[GROUPS];
+    const int grp = threadIdx.x / G;
+    const int wl = threadIdx.x & 31;                               // lane within the warp
+    const int leader = wl & ~(G - 1);
+    const uint32_t gmask = (G == 32) ? 0xFFFFFFFFu : (((1u << G) - 1u) << leader);
+
+    DecStream<G> st;
+    st.ring = &rings[grp]; st.lane = wl - leader; st.gmask = gmask;
+    for (int s = 0; s < DEC_SLOTS; s++) st.uses[s] = 0;
+    if (st.lane == 0) {
+        for (int s = 0; s < DEC_SLOTS; s++) simt::mbar_init(&st.ring->bar[s], 1);
+        simt::fence_mbar_init();
+    }
+    simt::syncwarp(gmask);
+
+    for (;;) {
+        uint32_t b = 0;
+        if (st.lane == 0) b = atomicAdd(counter, 1u);
+        b = simt::shfl(gmask, b, leader);
+        if (b >= (uint32_t)a.n_blocks) break;
+        const int r = decode_block<G, KNOWN>(st, a.src + a.src_off[b], a.src_len[b], a.dst + a.dst_off[b], a.dst_cap[b]);
+        if (st.lane == 0) a.out_len[b] = r;
+    }
+}
+
+template <int G, bool KNOWN>
+static cudaError_t launch_one(const BatchArgs& a, uint32_t* counter, const DeviceInfo& dev, cudaStream_t stream)
+{
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lz4_decode_kernel<G, KNOWN>, DEC_THREADS, 0);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    constexpr int GROUPS = DEC_THREADS / G;
+    long long want = ((long long)a.n_blocks + GROUPS - 1) / GROUPS;
+    long long grid = (long long)dev.num_sms * per_sm;
+    if (grid > want) grid = want;
+    if (grid < 1) grid = 1;
+    lz4_decode_kernel<G, KNOWN><<<(unsigned)grid, DEC_THREADS, 0, stream>>>(a, counter);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_decode(const BatchArgs& a, bool known_len, int lanes, uint32_t* counter,
+                          const DeviceInfo& dev, cudaStream_t stream, int64_t* launches)
+{
+    if (a.n_blocks <= 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), stream);
+    if (e != cudaSuccess) return e;
+    if (launches) ++*launches;
+    switch (lanes) {
+    case 8:  return known_len ? launch_one<8, true>(a, counter, dev, stream)  : launch_one<8, false>(a, counter, dev, stream);
+    case 16: return known_len ? launch_one<16, true>(a, counter, dev, stream) : launch_one<16, false>(a, counter, dev, stream);
+    default: return known_len ? launch_one<32, true>(a, counter, dev, stream) : launch_one<32, false>(a, counter, dev, stream);
+    }
+}
+
+}  // namespace lz4b200

@@ -1,0 +1,95 @@
+// simt.cuh -- the handful of warp / memory primitives the codec kernels are written against.
+//
+// Device build (nvcc, sm_100a): thin wrappers over the hardware instructions (SHFL / VOTE / MATCH, LDG/STG with
+// cache hints, cp.async.bulk + mbarrier for TMA-style staging -> SASS UBLKCP / SYNCS).
+// Test build (-DLZ4B200_SIMT_EMU, g++): the same names come from tests/simt_emu/simt_emu.h, a coroutine emulation
+// of one warp used only by the CPU-side logic tests.  The product library is never built that way.
+#pragma once
+#include <stdint.h>
+
+#if defined(LZ4B200_SIMT_EMU)
+#include "simt_emu.h"
+#else
+
+#include <cuda_runtime.h>
+#define SIMT_DEV __device__ __forceinline__
+#define SIMT_MEM __device__ __forceinline__
+
+namespace simt {
+
+SIMT_DEV uint32_t shfl(uint32_t mask, uint32_t v, int src) { return __shfl_sync(mask, v, src); }
+SIMT_DEV uint32_t ballot(uint32_t mask, bool p) { return __ballot_sync(mask, p); }
+SIMT_DEV uint32_t match_any(uint32_t mask, uint32_t v) { return __match_any_sync(mask, v); }
+SIMT_DEV void syncwarp(uint32_t mask) { __syncwarp(mask); }
+SIMT_DEV int ffs(uint32_t v) { return __ffs((int)v); }
+SIMT_DEV int clz(uint32_t v) { return __clz((int)v); }
+SIMT_DEV int popc(uint32_t v) { return __popc(v); }
+SIMT_DEV uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) { return __funnelshift_r(lo, hi, sh); }
+
+// coherent loads (data this kernel wrote earlier: decoder back-references)
+// (plain ld.global -- L1-cacheable; the asm "memory" clobber only stops the compiler from hoisting it over the
+//  __syncwarp() that orders it after another lane's store)
+SIMT_DEV uint8_t  ldg_u8(const uint8_t* p)
+{
+    uint32_t r;
+    asm volatile("ld.global.u8 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
+    return (uint8_t)r;
+}
+SIMT_DEV uint32_t ldg_u32(const void* p)
+{
+    uint32_t r;
+    asm volatile("ld.global.u32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
+    return r;
+}
+SIMT_DEV uint4    ldg_v4(const void* p)
+{
+    uint4 r;
+    asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+    return r;
+}
+// read-only path (kernel inputs)
+SIMT_DEV uint8_t  ldg_nc_u8(const uint8_t* p) { return __ldg(p); }
+SIMT_DEV uint32_t ldg_nc_u32(const void* p) { return __ldg((const uint32_t*)p); }
+SIMT_DEV uint4    ldg_nc_v4(const void* p) { return __ldg((const uint4*)p); }
+SIMT_DEV void stg_u8(uint8_t* p, uint8_t v) { *p = v; }
+SIMT_DEV void stg_u32(void* p, uint32_t v) { *(uint32_t*)p = v; }
+SIMT_DEV void stg_v4(void* p, uint4 v) { *(uint4*)p = v; }
+
+// ---- mbarrier + 1-D bulk async copy (global -> shared::cta), the TMA engine's non-tensor form --------------
+struct mbar_t { uint64_t v; };
+
+SIMT_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+SIMT_DEV void mbar_init(mbar_t* b, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(b)), "r"(count) : "memory");
+}
+SIMT_DEV void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// one thread: arm the barrier with the byte count, then launch the copy that will complete_tx on it
+SIMT_DEV void bulk_g2s(void* sdst, const void* gsrc, uint32_t bytes, mbar_t* b)
+{
+    uint32_t bar = smem_u32(b);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
+}
+SIMT_DEV void mbar_wait(mbar_t* b, uint32_t parity)
+{
+    uint32_t bar = smem_u32(b);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" :: "r"(bar), "r"(parity) : "memory");
+}
+
+}  // namespace simt
+#endif

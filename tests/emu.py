@@ -1,0 +1,89 @@
+"""ctypes driver for the CPU warp emulator (tests/simt_emu) -- TEST INFRASTRUCTURE ONLY.
+
+It compiles the *kernel headers themselves* (lz4net_b200/csrc/*.cuh) with g++ in emulation mode so that the
+warp-level algorithms can be checked against the oracle in a container without a GPU.  Nothing here is a product
+code path: liblz4b200.so contains no CPU codec.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+_DIR = os.path.join(_HERE, "simt_emu")
+_SO = os.path.join(_DIR, "libsimt_emu.so")
+_lib = None
+
+
+def _sources():
+    csrc = os.path.join(_ROOT, "lz4net_b200", "csrc")
+    return [os.path.join(_DIR, f) for f in ("simt_emu.cpp", "emu_harness.cpp", "simt_emu.h")] + \
+           [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".cuh")]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in _sources()):
+            subprocess.check_call(["g++", "-O2", "-g", "-shared", "-fPIC", "-std=c++17", "-DLZ4B200_SIMT_EMU",
+                                   "-I" + _DIR, "-I" + os.path.join(_ROOT, "lz4net_b200", "csrc"), "-o", _SO,
+                                   os.path.join(_DIR, "simt_emu.cpp"), os.path.join(_DIR, "emu_harness.cpp")])
+        _lib = C.CDLL(_SO)
+    return _lib
+
+
+def _ptr_array(arrs):
+    return (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+
+
+def decode(blocks, caps, lanes=32, known=True, sched_seed=1, src_skew=0):
+    """blocks: list of bytes (compressed); caps: list of int. Returns (results, outputs).  src_skew shifts the
+    compressed bytes inside their buffer to exercise unaligned stream starts."""
+    n = len(blocks)
+    srcs = []
+    for b in blocks:
+        a = np.zeros(src_skew + len(b) + 64, np.uint8)
+        a[src_skew:src_skew + len(b)] = np.frombuffer(b, np.uint8)
+        srcs.append(a)
+    dsts = [np.full(max(c, 0) + 96, 0xCD, np.uint8) for c in caps]
+    isz = np.array([len(b) for b in blocks], np.int32)
+    cps = np.array(caps, np.int32)
+    res = np.zeros(n, np.int32)
+    sp = (C.c_void_p * n)(*[a.ctypes.data + src_skew for a in srcs])
+    dp = (C.c_void_p * n)(*[a.ctypes.data + 32 for a in dsts])       # 32-byte red zone in front
+    lib().emu_decode(lanes, int(known), n, sp, isz.ctypes.data_as(C.c_void_p), dp, cps.ctypes.data_as(C.c_void_p),
+                     res.ctypes.data_as(C.c_void_p), C.c_uint64(sched_seed))
+    outs = []
+    for d, c in zip(dsts, caps):
+        assert (d[:32] == 0xCD).all() and (d[32 + max(c, 0):] == 0xCD).all(), "decoder wrote outside [dst, dst+cap)"
+        outs.append(d[32:32 + max(c, 0)].tobytes())
+    return res.tolist(), outs
+
+
+def encode(blocks, caps=None, sched_seed=1, src_skew=0, dst_skew=0):
+    n = len(blocks)
+    if caps is None:
+        caps = [len(b) + len(b) // 255 + 16 for b in blocks]
+    srcs = []
+    for b in blocks:
+        a = np.zeros(src_skew + len(b) + 64, np.uint8)
+        a[src_skew:src_skew + len(b)] = np.frombuffer(b, np.uint8)
+        srcs.append(a)
+    dsts = [np.full(max(c, 0) + 96 + dst_skew, 0xCD, np.uint8) for c in caps]
+    ns = np.array([len(b) for b in blocks], np.int32)
+    cps = np.array(caps, np.int32)
+    res = np.zeros(n, np.int32)
+    sp = (C.c_void_p * n)(*[a.ctypes.data + src_skew for a in srcs])
+    dp = (C.c_void_p * n)(*[a.ctypes.data + 32 + dst_skew for a in dsts])
+    lib().emu_encode(n, sp, ns.ctypes.data_as(C.c_void_p), dp, cps.ctypes.data_as(C.c_void_p),
+                     res.ctypes.data_as(C.c_void_p), C.c_uint64(sched_seed))
+    outs = []
+    for d, c, r in zip(dsts, caps, res.tolist()):
+        lo = 32 + dst_skew
+        assert (d[:lo] == 0xCD).all() and (d[lo + max(c, 0):] == 0xCD).all(), "encoder wrote outside [dst, dst+cap)"
+        outs.append(d[lo:lo + max(r, 0)].tobytes())
+    return res.tolist(), outs

@@ -1,0 +1,81 @@
+// TEST INFRASTRUCTURE ONLY: compiles the kernel headers of lz4net_b200/csrc in emulation mode (see simt_emu.h) and
+// exposes them to the CPU-side pytest suite through a C interface.  Not part of the product.
+#define LZ4B200_SIMT_EMU 1
+#include "simt_emu.h"
+#include "lz4_decode.cuh"
+#include "lz4_encode.cuh"
+#include <stdlib.h>
+#include <vector>
+
+using namespace lz4b200;
+
+namespace {
+
+struct DecJob {
+    int G; bool known; int nblocks;
+    const uint8_t* const* src; const int* isize; uint8_t* const* dst; const int* cap; int* result;
+    DecRing rings[4];
+};
+
+template <int G, bool KNOWN>
+void dec_lane(int wl, DecJob* j)
+{
+    const int leader = wl & ~(G - 1);
+    const int grp = wl / G;
+    const uint32_t gmask = (G == 32) ? 0xFFFFFFFFu : (((1u << G) - 1u) << leader);
+    DecStream<G> st;
+    st.ring = &j->rings[grp]; st.lane = wl - leader; st.gmask = gmask;
+    for (int s = 0; s < DEC_SLOTS; s++) st.uses[s] = 0;
+    // every group walks the block list with a stride, like the kernel's dynamic hand-out
+    for (int b = grp; b < j->nblocks; b += 32 / G) {
+        int r = decode_block<G, KNOWN>(st, j->src[b], j->isize[b], j->dst[b], j->cap[b]);
+        if (st.lane == 0) j->result[b] = r;
+    }
+}
+
+void dec_entry(int lane, void* arg)
+{
+    DecJob* j = (DecJob*)arg;
+    switch (j->G) {
+    case 8:  j->known ? dec_lane<8, true>(lane, j)  : dec_lane<8, false>(lane, j); break;
+    case 16: j->known ? dec_lane<16, true>(lane, j) : dec_lane<16, false>(lane, j); break;
+    default: j->known ? dec_lane<32, true>(lane, j) : dec_lane<32, false>(lane, j); break;
+    }
+}
+
+struct EncJob {
+    int nblocks; const uint8_t* const* src; const int* n; uint8_t* const* dst; const int* cap; int* result;
+    EncShared* sh;
+};
+
+void enc_entry(int lane, void* arg)
+{
+    EncJob* j = (EncJob*)arg;
+    for (int b = 0; b < j->nblocks; b++) {
+        int r = encode_block(j->sh, j->src[b], j->n[b], j->dst[b], j->cap[b], lane);
+        if (lane == 0) j->result[b] = r;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+void emu_decode(int G, int known, int nblocks, const uint8_t* const* src, const int* isize,
+                uint8_t* const* dst, const int* cap, int* result, uint64_t sched_seed)
+{
+    DecJob* j = new DecJob();
+    j->G = G; j->known = known != 0; j->nblocks = nblocks; j->src = src; j->isize = isize; j->dst = dst; j->cap = cap; j->result = result;
+    simt_emu::run_warp(dec_entry, j, sched_seed);
+    delete j;
+}
+
+void emu_encode(int nblocks, const uint8_t* const* src, const int* n, uint8_t* const* dst, const int* cap,
+                int* result, uint64_t sched_seed)
+{
+    EncJob j{nblocks, src, n, dst, cap, result, (EncShared*)aligned_alloc(16, sizeof(EncShared))};
+    simt_emu::run_warp(enc_entry, &j, sched_seed);
+    free(j.sh);
+}
+
+}

@@ -1,0 +1,56 @@
+/*
+ * simt_emu.h -- TEST INFRASTRUCTURE ONLY.
+ *
+ * A tiny CPU emulation of one CUDA warp so that the *kernel source itself* (lz4net_b200/csrc/*.cuh) can be
+ * compiled with g++ and exercised by `pytest -m "not gpu"` in a container that has no GPU: each lane runs as a
+ * ucontext coroutine; every warp collective (shfl / ballot / match_any / syncwarp) is a rendezvous of the lanes
+ * named in its mask.  Lanes are scheduled in a seeded pseudo-random order between collectives, so code that relies
+ * on lock-step execution without a __syncwarp() is likely to show up as a mismatch here.
+ * It is never linked into liblz4b200.so and is not a product code path (there is no CPU fallback).
+ */
+#pragma once
+#include <stdint.h>
+#include <string.h>
+
+struct uint4 { uint32_t x, y, z, w; };
+struct uint2 { uint32_t x, y; };
+
+namespace simt_emu {
+// run `fn(lane, arg)` on 32 lanes as one warp
+void run_warp(void (*fn)(int lane, void* arg), void* arg, uint64_t sched_seed);
+uint32_t collective(int op, uint32_t mask, uint32_t a, uint32_t b);
+int current_lane();
+void yield();          // let the other lanes run (used by emulated spin-waits)
+enum { OP_SYNC = 0, OP_BALLOT = 1, OP_SHFL = 2, OP_MATCH = 3 };
+}
+
+namespace simt {
+static inline uint32_t shfl(uint32_t mask, uint32_t v, int src) { return simt_emu::collective(simt_emu::OP_SHFL, mask, v, (uint32_t)src); }
+static inline uint32_t ballot(uint32_t mask, bool p) { return simt_emu::collective(simt_emu::OP_BALLOT, mask, p ? 1u : 0u, 0); }
+static inline uint32_t match_any(uint32_t mask, uint32_t v) { return simt_emu::collective(simt_emu::OP_MATCH, mask, v, 0); }
+static inline void syncwarp(uint32_t mask) { simt_emu::collective(simt_emu::OP_SYNC, mask, 0, 0); }
+static inline int ffs(uint32_t v) { return __builtin_ffs((int)v); }
+static inline int clz(uint32_t v) { return v ? __builtin_clz(v) : 32; }
+static inline int popc(uint32_t v) { return __builtin_popcount(v); }
+static inline uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) { uint64_t t = ((uint64_t)hi << 32) | lo; return (uint32_t)(t >> (sh & 31)); }
+
+static inline uint8_t  ldg_u8(const uint8_t* p) { return *p; }
+static inline uint32_t ldg_u32(const void* p) { uint32_t v; memcpy(&v, p, 4); return v; }
+static inline uint4    ldg_v4(const void* p) { uint4 v; memcpy(&v, p, 16); return v; }
+static inline uint8_t  ldg_nc_u8(const uint8_t* p) { return *p; }
+static inline uint32_t ldg_nc_u32(const void* p) { return ldg_u32(p); }
+static inline uint4    ldg_nc_v4(const void* p) { return ldg_v4(p); }
+static inline void stg_u8(uint8_t* p, uint8_t v) { *p = v; }
+static inline void stg_u32(void* p, uint32_t v) { memcpy(p, &v, 4); }
+static inline void stg_v4(void* p, uint4 v) { memcpy(p, &v, 16); }
+
+// async bulk copy global -> shared with an mbarrier: immediate in the emulator
+struct mbar_t { uint64_t v; };
+static inline void mbar_init(mbar_t* b, int) { b->v = 0; }
+// the copy "lands" at once and completes one barrier phase; waiters poll the phase parity like mbarrier.try_wait.parity
+static inline void bulk_g2s(void* sdst, const void* gsrc, uint32_t bytes, mbar_t* b) { memcpy(sdst, gsrc, bytes); b->v++; }
+static inline void mbar_wait(mbar_t* b, uint32_t parity) { while ((b->v & 1) == (parity & 1)) simt_emu::yield(); }
+static inline void fence_mbar_init() {}
+}
+#define SIMT_DEV static inline
+#define SIMT_MEM inline

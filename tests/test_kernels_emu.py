@@ -1,0 +1,158 @@
+"""CPU-only logic tests of the CUDA kernel source, run through the warp emulator (tests/simt_emu).
+
+The kernels' algorithms (lz4net_b200/csrc/lz4_decode.cuh, lz4_encode.cuh, lz4_copy.cuh) are compiled with g++ in
+emulation mode and compared with the oracle -- the same checks the `-m gpu` parity tests make on the B200 through the
+C ABI, at sizes the emulator finishes in seconds.  Shape: lz4net's ConformanceTests (byte-identical encoders, every
+decoder round-trips, src/LZ4.Tests/ConformanceTests.cs:57-148) + the upstream fuzzer's size +-1 invariants
+(original/fuzzer.c:176-227)."""
+import numpy as np
+import pytest
+
+import oracle
+from tests import cases, emu
+
+
+def _enc_check(blocks, caps=None, **kw):
+    res, outs = emu.encode(blocks, caps, **kw)
+    for i, b in enumerate(blocks):
+        cap = None if caps is None else caps[i]
+        r, o = oracle.encode(b, cap=cap)
+        assert (res[i], outs[i]) == (r, o), (i, len(b), cap, res[i], r)
+
+
+@pytest.mark.parametrize("model", cases.MODELS)
+def test_encode_matches_oracle_64k_and_random_lengths(model):
+    lens = [65536] + cases.random_lengths(10, 65546, seed=21) + [65546, 65535]
+    blocks = [cases.content(model, n, seed=300 + i).tobytes() for i, n in enumerate(lens)]
+    _enc_check(blocks, sched_seed=5)
+
+
+def test_encode_boundary_lengths():
+    blocks = []
+    for n in cases.BOUNDARY_LENGTHS:
+        if n <= 65546:
+            for m in ("lowent", "periodic", "E50"):
+                blocks.append(cases.content(m, n, seed=n).tobytes())
+    _enc_check(blocks, sched_seed=9)
+
+
+def test_encode_limited_output():
+    """cap = exactly enough / one short / n (LZ4Stream, Wrap) / tiny: same return value and bytes, no overrun."""
+    blocks, caps = [], []
+    for i, m in enumerate(cases.MODELS):
+        for n in (200, 3000, 65536):
+            d = cases.content(m, n, seed=40 + i).tobytes()
+            r, _ = oracle.encode(d)
+            for cap in (r, r - 1, n, n - 1, r // 2, 0, 1, 7, 8, 13):
+                if cap >= 0:
+                    blocks.append(d); caps.append(cap)
+    _enc_check(blocks, caps, sched_seed=3)
+
+
+def test_encode_general_variant_above_64k():
+    """n >= 65547 takes LZ4_compressCtx (original/lz4.c:345-562): 12-bit hash, u32 table, distance checks."""
+    blocks = [cases.content(m, n, seed=7).tobytes()
+              for m, n in (("ETEXT", 65547), ("lowent", 70001), ("E50", 150000), ("periodic", 140000), ("mixed", 69999),
+                           ("E100", 200000), ("runs", 131072), ("E0", 66000))]
+    _enc_check(blocks, sched_seed=2)
+    caps = [oracle.encode(b)[0] - 1 for b in blocks]
+    _enc_check(blocks, caps, sched_seed=4)
+
+
+@pytest.mark.parametrize("skew", [1, 3, 7, 13])
+def test_encode_unaligned_buffers(skew):
+    blocks = [cases.content(m, 5000 + skew, seed=skew).tobytes() for m in cases.MODELS]
+    res, outs = emu.encode(blocks, sched_seed=skew, src_skew=skew, dst_skew=16 - skew)
+    for b, r, o in zip(blocks, res, outs):
+        assert (r, o) == oracle.encode(b)
+
+
+def test_encode_schedule_independent():
+    """Lanes are scheduled in different orders: the result may not depend on lock-step luck."""
+    blocks = [cases.content("lowent", 20000, seed=1).tobytes(), cases.content("mixed", 20000, seed=2).tobytes()]
+    for seed in range(1, 6):
+        _enc_check(blocks, sched_seed=seed)
+
+
+@pytest.mark.parametrize("lanes", [32, 16, 8])
+@pytest.mark.parametrize("known", [True, False])
+def test_decode_matches_oracle(lanes, known):
+    blocks, raws = [], []
+    for i, m in enumerate(cases.MODELS):
+        for n in (65536, 1, 12, 13, 700, 33000):
+            d = cases.content(m, n, seed=60 + i).tobytes()
+            for fn in (oracle.encode, oracle.encode_hc):
+                blocks.append(fn(d)[1]); raws.append(d)
+    res, outs = emu.decode(blocks, [len(r) for r in raws], lanes=lanes, known=known, sched_seed=lanes)
+    for c, d, r, o in zip(blocks, raws, res, outs):
+        assert r == (len(c) if known else len(d)), (len(d), r)
+        assert o == d
+
+
+@pytest.mark.parametrize("lanes", [32, 8])
+def test_decode_size_invariants(lanes):
+    """fuzzer.c:176-210 -- exact size works; size +-1 fails; verdicts equal the oracle's (which is pinned to the reference)."""
+    from lz4net_b200 import synth
+    comp, caps, known_flags, expect = [], [], [], []
+    for seed in range(6):
+        d = synth.fuz_block(seed, 6000).tobytes()
+        c = oracle.encode(d)[1]
+        n = len(d)
+        for osz in (n, n - 1, n + 1):
+            comp.append(c); caps.append(osz); known_flags.append(True); expect.append(oracle.decode_known(c, osz)[0])
+        for cc, osz in ((c, n + 1), (c, n), (c, n - 1), (c[:-1], n), (c + b"\0", n)):
+            comp.append(cc); caps.append(osz); known_flags.append(False); expect.append(oracle.decode_unknown(cc, osz)[0])
+    for known in (True, False):
+        idx = [i for i, k in enumerate(known_flags) if k == known]
+        res, _ = emu.decode([comp[i] for i in idx], [caps[i] for i in idx], lanes=lanes, known=known, sched_seed=11)
+        for i, r in zip(idx, res):
+            assert (r < 0) == (expect[i] < 0), (i, r, expect[i])
+            if expect[i] >= 0:
+                assert r == expect[i]
+
+
+@pytest.mark.parametrize("known", [True, False])
+def test_decode_corrupt_streams_never_escape(known):
+    """Bit flips / truncations: same accept-reject verdict as the oracle, identical bytes when accepted, and no write
+    outside [dst, dst+cap) (emu.decode asserts the red zones)."""
+    rng = np.random.default_rng(5)
+    comp, caps = [], []
+    for i in range(120):
+        d = cases.content("mixed", 2500, seed=i).tobytes()
+        c = bytearray(oracle.encode(d)[1])
+        kind = i % 3
+        if kind == 0:
+            for _ in range(int(rng.integers(1, 4))):
+                c[int(rng.integers(0, len(c)))] ^= 1 << int(rng.integers(0, 8))
+        elif kind == 1:
+            c = c[: int(rng.integers(1, len(c)))]
+        else:
+            c[int(rng.integers(0, len(c)))] = 0xFF
+        comp.append(bytes(c)); caps.append(len(d))
+    res, outs = emu.decode(comp, caps, lanes=32, known=known, sched_seed=13)
+    for c, cap, r, o in zip(comp, caps, res, outs):
+        er, eo = (oracle.decode_known if known else oracle.decode_unknown)(c, cap)
+        assert (r < 0) == (er < 0), (r, er)
+        if er >= 0:
+            assert r == er and o[:len(eo)] == eo
+
+
+@pytest.mark.parametrize("skew", [1, 5, 15])
+def test_decode_unaligned_stream_start(skew):
+    raws = [cases.content(m, 9000, seed=skew).tobytes() for m in cases.MODELS]
+    comp = [oracle.encode(d)[1] for d in raws]
+    res, outs = emu.decode(comp, [len(d) for d in raws], lanes=16, known=True, sched_seed=skew, src_skew=skew)
+    assert outs == raws and res == [len(c) for c in comp]
+
+
+def test_decode_long_overlapping_matches():
+    """RLE-style matches (offset < length), every small offset, long enough to take the wide path."""
+    raws = []
+    for off in list(range(1, 40)) + [63, 64, 65, 255, 256, 511, 512, 527, 528, 529, 1000]:
+        rng = np.random.default_rng(off)
+        pat = rng.integers(0, 256, off, dtype=np.uint8)
+        raws.append(np.tile(pat, 9000 // off + 2)[:9000].tobytes())
+    comp = [oracle.encode(d)[1] for d in raws]
+    for lanes in (32, 16, 8):
+        res, outs = emu.decode(comp, [len(d) for d in raws], lanes=lanes, known=True, sched_seed=lanes)
+        assert outs == raws
