@@ -40,6 +40,7 @@ extern "C" {
 #define LZ4B200_E_NODEVICE   -2        /* no CUDA device, or not compute capability 10.x */
 #define LZ4B200_E_CUDA       -3        /* a CUDA runtime call failed; see lz4b200_last_error() */
 #define LZ4B200_E_NOMEM      -4
+#define LZ4B200_E_FORMAT     -5        /* malformed LZ4Stream / Wrap framing, or a chunk that does not decode */
 
 typedef struct lz4b200_ctx lz4b200_ctx;
 

@@ -1,0 +1,290 @@
+"""Python mirror of lz4net's public surface for the accelerated path, over the C ABI.
+
+Names, argument meaning and error behaviour follow the reference:
+
+* ``LZ4Codec.Encode / EncodeHC / Decode / MaximumOutputLength / Wrap / WrapHC / Unwrap``  (src/LZ4/LZ4Codec.cs:313-440,510-599)
+  with the C# boundary conventions: ``Encode`` of an empty input returns 0 (src/LZ4ps/LZ4Codec.cs:156-160),
+  ``EncodeHC`` failure is -1 (src/LZ4ps/LZ4Codec.Safe.cs:721-723), a decode error raises (``ArgumentException`` there,
+  ``ValueError`` here; src/LZ4ps/LZ4Codec.Safe.cs:539-549).
+* ``CudaLZ4Service`` -- the ``ILZ4Service`` (src/LZ4/ILZ4Service.cs:30-36) implementation a maintainer would register.
+* ``BlockBatch`` helpers -- the batched entry points, for torch CUDA tensors (device memory) or numpy arrays (host).
+
+torch is used only to own device memory / streams; every call goes through ``liblz4b200.so`` with raw pointers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import native
+
+_default_ctx = None
+
+
+class Context:
+    """Owns one lz4b200_ctx (one GPU)."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        native.check(native.lib().lz4b200_create(C.byref(self._h), int(device)), "lz4b200_create")
+        self.device = int(device)
+
+    def close(self):
+        if self._h:
+            native.lib().lz4b200_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def set_option(self, key: str, value: int):
+        native.check(native.lib().lz4b200_set_option(self._h, key.encode(), int(value)), f"set_option({key})")
+
+    def synchronize(self):
+        native.check(native.lib().lz4b200_synchronize(self._h), "synchronize")
+
+    @property
+    def launches(self) -> int:
+        return int(native.lib().lz4b200_launch_count(self._h))
+
+    # ---- batched calls on raw pointers -------------------------------------------------------------------------
+    def encode_batch_ptr(self, src, src_off, src_len, dst, dst_off, dst_cap, out_len, n, hc=False, device=True, stream=0):
+        native.check(native.lib().lz4b200_encode_batch(self._h, src, src_off, src_len, dst, dst_off, dst_cap, out_len, int(n),
+                                                       native.MODE_HC if hc else native.MODE_FAST,
+                                                       native.MEM_DEVICE if device else native.MEM_HOST, stream), "encode_batch")
+
+    def decode_batch_ptr(self, src, src_off, src_len, dst, dst_off, dst_cap, out_len, n, known=True, device=True, stream=0):
+        native.check(native.lib().lz4b200_decode_batch(self._h, src, src_off, src_len, dst, dst_off, dst_cap, out_len, int(n),
+                                                       1 if known else 0,
+                                                       native.MEM_DEVICE if device else native.MEM_HOST, stream), "decode_batch")
+
+    # ---- numpy (host memory) convenience -----------------------------------------------------------------------
+    def encode_blocks(self, blocks, caps=None, hc=False):
+        """blocks: list of bytes-like.  Returns (out_len list, list of bytes) -- one host-memory batch call."""
+        n = len(blocks)
+        lens = np.array([len(b) for b in blocks], np.int32)
+        caps = np.array([native.lib().lz4b200_compress_bound(int(l)) for l in lens] if caps is None else caps, np.int32)
+        src_off = np.concatenate([[0], np.cumsum(lens, dtype=np.int64)[:-1]]).astype(np.int64) if n else np.zeros(0, np.int64)
+        dst_off = np.concatenate([[0], np.cumsum(caps, dtype=np.int64)[:-1]]).astype(np.int64) if n else np.zeros(0, np.int64)
+        src = np.frombuffer(b"".join(bytes(b) for b in blocks) + b"\0" * 16, np.uint8)
+        dst = np.full(int(caps.sum()) + 16, 0xEE, np.uint8)
+        out = np.zeros(n, np.int32)
+        if n:
+            self.encode_batch_ptr(src.ctypes.data, src_off.ctypes.data, lens.ctypes.data, dst.ctypes.data, dst_off.ctypes.data,
+                                  caps.ctypes.data, out.ctypes.data, n, hc=hc, device=False)
+        return out.tolist(), [dst[int(o):int(o) + max(int(r), 0)].tobytes() for o, r in zip(dst_off, out)]
+
+    def decode_blocks(self, blocks, caps, known=True):
+        n = len(blocks)
+        lens = np.array([len(b) for b in blocks], np.int32)
+        caps = np.array(caps, np.int32)
+        src_off = np.concatenate([[0], np.cumsum(lens, dtype=np.int64)[:-1]]).astype(np.int64) if n else np.zeros(0, np.int64)
+        dst_off = np.concatenate([[0], np.cumsum(caps, dtype=np.int64)[:-1]]).astype(np.int64) if n else np.zeros(0, np.int64)
+        src = np.frombuffer(b"".join(bytes(b) for b in blocks) + b"\0" * 16, np.uint8)
+        dst = np.zeros(int(caps.sum()) + 16, np.uint8)
+        out = np.zeros(n, np.int32)
+        if n:
+            self.decode_batch_ptr(src.ctypes.data, src_off.ctypes.data, lens.ctypes.data, dst.ctypes.data, dst_off.ctypes.data,
+                                  caps.ctypes.data, out.ctypes.data, n, known=known, device=False)
+        res = out.tolist()
+        outs = []
+        for o, c, r in zip(dst_off, caps, res):
+            m = int(c) if known else max(int(r), 0)
+            outs.append(dst[int(o):int(o) + m].tobytes())
+        return res, outs
+
+    # ---- framing ----------------------------------------------------------------------------------------------
+    def stream_encode(self, data: bytes, block_size: int = 1 << 20, high_compression: bool = False) -> bytes:
+        """The bytes LZ4Stream(inner, Compress, highCompression, blockSize) emits for Write(data); Close()."""
+        l = native.lib()
+        src = np.frombuffer(bytes(data) + b"\0", np.uint8)
+        cap = int(l.lz4b200_stream_bound(len(data), block_size))
+        dst = np.zeros(cap + 16, np.uint8)
+        w = l.lz4b200_stream_encode(self._h, src.ctypes.data, len(data), block_size, int(high_compression), dst.ctypes.data, cap)
+        if w < 0:
+            raise native.Lz4B200Error(f"stream_encode failed ({w}): {native.last_error()}")
+        return dst[:w].tobytes()
+
+    def stream_decode(self, data: bytes) -> bytes:
+        l = native.lib()
+        src = np.frombuffer(bytes(data) + b"\0", np.uint8)
+        total = int(l.lz4b200_stream_decoded_size(src.ctypes.data, len(data)))
+        if total < 0:
+            raise EOFError("LZ4Stream: unexpected end of stream / corrupt chunk header")     # EndOfStreamException
+        dst = np.zeros(total + 16, np.uint8)
+        r = l.lz4b200_stream_decode(self._h, src.ctypes.data, len(data), dst.ctypes.data, total)
+        if r == native.E_FORMAT:
+            raise ValueError("LZ4 block has been corrupted")
+        if r < 0:
+            raise native.Lz4B200Error(f"stream_decode failed ({r}): {native.last_error()}")
+        return dst[:total].tobytes()
+
+
+def default_context() -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        dev = 0
+        try:
+            import torch
+            if torch.cuda.is_available():
+                dev = torch.cuda.current_device()
+        except Exception:
+            pass
+        _default_ctx = Context(dev)
+    return _default_ctx
+
+
+class CudaLZ4Service:
+    """ILZ4Service (src/LZ4/ILZ4Service.cs:30-36) over the single-block C entry points."""
+
+    CodecName = "CUDA sm_100a"
+
+    @staticmethod
+    def _ptr(buf, offset):
+        a = np.frombuffer(buf, np.uint8) if not isinstance(buf, np.ndarray) else buf
+        return a, a.ctypes.data + offset
+
+    def Encode(self, input, inputOffset, inputLength, output, outputOffset, outputLength) -> int:
+        _, sp = self._ptr(input, inputOffset)
+        _, dp = self._ptr(output, outputOffset)
+        return int(native.lib().lz4b200_compress_limitedOutput(sp, dp, inputLength, outputLength))
+
+    def EncodeHC(self, input, inputOffset, inputLength, output, outputOffset, outputLength) -> int:
+        _, sp = self._ptr(input, inputOffset)
+        _, dp = self._ptr(output, outputOffset)
+        r = int(native.lib().lz4b200_compressHC_limitedOutput(sp, dp, inputLength, outputLength))
+        return r if r > 0 else -1                                    # src/LZ4ps/LZ4Codec.Safe.cs:721-723
+
+    def Decode(self, input, inputOffset, inputLength, output, outputOffset, outputLength, knownOutputLength) -> int:
+        _, sp = self._ptr(input, inputOffset)
+        _, dp = self._ptr(output, outputOffset)
+        if knownOutputLength:
+            r = int(native.lib().lz4b200_uncompress(sp, dp, inputLength, outputLength))
+            if r != inputLength:                                     # src/LZ4ps/LZ4Codec.Safe.cs:539-542
+                raise ValueError("LZ4 block is corrupted, or invalid length has been given.")
+            return outputLength
+        r = int(native.lib().lz4b200_uncompress_unknownOutputSize(sp, dp, inputLength, outputLength))
+        if r < 0:                                                    # :546-549
+            raise ValueError("LZ4 block is corrupted, or invalid length has been given.")
+        return r
+
+
+class LZ4Codec:
+    """Static facade, src/LZ4/LZ4Codec.cs.  Buffers are bytearray / numpy uint8 arrays (the byte[] of the original)."""
+
+    _service = CudaLZ4Service()
+    CodecName = "CUDA sm_100a/CUDA sm_100a/CUDA sm_100aHC"
+
+    @staticmethod
+    def MaximumOutputLength(inputLength: int) -> int:                # :313-316
+        return inputLength + inputLength // 255 + 16
+
+    @staticmethod
+    def _check(buf, offset, length, what):                           # src/LZ4ps/LZ4Codec.cs:151-170
+        if buf is None:
+            raise TypeError(f"{what} is null")
+        if length < 0:
+            length = len(buf) - offset
+        if offset < 0 or offset + length > len(buf):
+            raise ValueError(f"{what}Offset and {what}Length are invalid for given {what}")
+        return length
+
+    @classmethod
+    def Encode(cls, input, inputOffset=0, inputLength=-1, output=None, outputOffset=0, outputLength=-1):
+        if output is None:                                           # byte[] Encode(byte[], int, int)  :344-365
+            inputLength = cls._check(input, inputOffset, inputLength, "input")
+            if inputLength == 0:
+                return bytes()
+            out = bytearray(cls.MaximumOutputLength(inputLength))
+            n = cls.Encode(input, inputOffset, inputLength, out, 0, len(out))
+            if n < 0:
+                raise ValueError("Compression has been corrupted")
+            return bytes(out[:n])
+        inputLength = cls._check(input, inputOffset, inputLength, "input")
+        outputLength = cls._check(output, outputOffset, outputLength, "output")
+        if inputLength == 0 or outputLength == 0:
+            return 0
+        return cls._service.Encode(input, inputOffset, inputLength, output, outputOffset, outputLength)
+
+    @classmethod
+    def EncodeHC(cls, input, inputOffset=0, inputLength=-1, output=None, outputOffset=0, outputLength=-1):
+        if output is None:
+            inputLength = cls._check(input, inputOffset, inputLength, "input")
+            if inputLength == 0:
+                return bytes()
+            out = bytearray(cls.MaximumOutputLength(inputLength))
+            n = cls.EncodeHC(input, inputOffset, inputLength, out, 0, len(out))
+            if n < 0:
+                raise ValueError("Compression has been corrupted")
+            return bytes(out[:n])
+        inputLength = cls._check(input, inputOffset, inputLength, "input")
+        outputLength = cls._check(output, outputOffset, outputLength, "output")
+        if inputLength == 0 or outputLength == 0:
+            return 0 if inputLength == 0 else -1
+        return cls._service.EncodeHC(input, inputOffset, inputLength, output, outputOffset, outputLength)
+
+    @classmethod
+    def Decode(cls, input, inputOffset, inputLength, output=None, outputOffset=0, outputLength=0, knownOutputLength=False):
+        if output is None or isinstance(output, int):                # byte[] Decode(byte[], int, int, int outputLength)  :448-462
+            want = outputOffset if output is None else output
+            inputLength = cls._check(input, inputOffset, inputLength, "input")
+            if inputLength == 0:
+                return bytes()
+            out = bytearray(want)
+            n = cls.Decode(input, inputOffset, inputLength, out, 0, want, True)
+            if n != want:
+                raise ValueError("outputLength is not valid")
+            return bytes(out)
+        inputLength = cls._check(input, inputOffset, inputLength, "input")
+        outputLength = cls._check(output, outputOffset, outputLength, "output")
+        if inputLength == 0:
+            return 0
+        return cls._service.Decode(input, inputOffset, inputLength, output, outputOffset, outputLength, knownOutputLength)
+
+    # ---- Wrap / Unwrap (:510-599) ------------------------------------------------------------------------------
+    @staticmethod
+    def _wrap(data, hc):
+        l = native.lib()
+        src = np.frombuffer(bytes(data) + b"\0", np.uint8)
+        dst = np.zeros(len(data) + 8 + 16, np.uint8)
+        r = l.lz4b200_wrap(default_context().handle, src.ctypes.data, len(data), int(hc), dst.ctypes.data, len(data) + 8)
+        if r < 0:
+            raise native.Lz4B200Error(f"wrap failed ({r}): {native.last_error()}")
+        return dst[:r].tobytes()
+
+    @classmethod
+    def Wrap(cls, inputBuffer, inputOffset=0, inputLength=2 ** 31 - 1):
+        inputLength = min(len(inputBuffer) - inputOffset, inputLength)
+        if inputLength < 0:
+            raise ValueError("inputBuffer size of inputLength is invalid")
+        return cls._wrap(bytes(inputBuffer[inputOffset:inputOffset + inputLength]), False)
+
+    @classmethod
+    def WrapHC(cls, inputBuffer, inputOffset=0, inputLength=2 ** 31 - 1):
+        inputLength = min(len(inputBuffer) - inputOffset, inputLength)
+        if inputLength < 0:
+            raise ValueError("inputBuffer size of inputLength is invalid")
+        return cls._wrap(bytes(inputBuffer[inputOffset:inputOffset + inputLength]), True)
+
+    @staticmethod
+    def Unwrap(inputBuffer, inputOffset=0):
+        l = native.lib()
+        data = bytes(inputBuffer[inputOffset:])
+        src = np.frombuffer(data + b"\0", np.uint8)
+        size = l.lz4b200_unwrap_size(src.ctypes.data, len(data))
+        if size < 0:
+            raise ValueError("inputBuffer size is invalid or has been corrupted")
+        dst = np.zeros(size + 16, np.uint8)
+        r = l.lz4b200_unwrap(default_context().handle, src.ctypes.data, len(data), dst.ctypes.data, size)
+        if r < 0:
+            raise ValueError("LZ4 block is corrupted, or invalid length has been given.")
+        return dst[:r].tobytes()

@@ -1,0 +1,395 @@
+// capi.cu -- the C ABI of liblz4b200.so (include/lz4b200.h): context, batched entry points, single-block entry points.
+//
+// Host-memory batches are processed as a software pipeline: the block list is cut into chunks, and for each chunk
+// H2D(inputs) -> kernel -> D2H(outputs) is enqueued on one of NSLOT streams, so that the copy engines (both PCIe
+// directions) and the SMs work on different chunks at the same time.  There is no CPU codec in this library: if the
+// device or the kernel image is unusable every entry point reports an error.
+#include "../../include/lz4b200.h"
+#include "kernels.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace lz4b200;
+
+namespace {
+
+thread_local std::string g_err = "";
+
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+int cuda_fail(cudaError_t e, const char* what)
+{
+    g_err = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+    return LZ4B200_E_CUDA;
+}
+#define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return cuda_fail(e_, #x); } while (0)
+
+constexpr int NSLOT = 3;                       // pipeline depth of host-memory batches
+constexpr int NCOUNTER = 256;
+constexpr size_t HOST_CHUNK_BYTES = 96u << 20; // raw bytes per pipeline stage
+
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + (n >> 3) + 4096;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+struct PinBuf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMallocHost(&p, n + 4096);
+        if (e == cudaSuccess) cap = n + 4096;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    DevBuf src, dst, meta;
+    PinBuf hmeta;
+};
+
+}  // namespace
+
+struct lz4b200_ctx {
+    int device = 0;
+    DeviceInfo dev{};
+    cudaStream_t stream = nullptr;
+    uint32_t* counters = nullptr;
+    int next_counter = 0;
+    DevBuf hc_arena, compact_tmp;
+    int decode_lanes = 32;
+    int encode_ctas_per_sm = 0;            // 0 = as many as shared memory allows
+    int hc_concurrency = 16384;
+    Slot slot[NSLOT];
+    int64_t launches = 0;
+    std::mutex mu;
+
+    uint32_t* counter() { uint32_t* c = counters + next_counter; next_counter = (next_counter + 1) % NCOUNTER; return c; }
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1; bool ok;
+    explicit DeviceGuard(int dev) { ok = cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int run_device(lz4b200_ctx* c, const BatchArgs& a, int op /*0 enc fast, 1 enc hc, 2 dec known, 3 dec unknown*/, cudaStream_t st)
+{
+    cudaError_t e = cudaSuccess;
+    switch (op) {
+    case 0: e = launch_encode_fast(a, c->counter(), c->encode_ctas_per_sm, c->dev, st, &c->launches); break;
+    case 1: {
+        const int conc = (int)std::min<int64_t>(c->hc_concurrency, std::max(a.n_blocks, 1));
+        const size_t need = hc_scratch_bytes(conc);
+        if (need > c->hc_arena.cap) {
+            CU(cudaDeviceSynchronize());           // the arena may still be in use by an earlier launch
+            CU(c->hc_arena.reserve(need));
+        }
+        e = launch_encode_hc(a, c->hc_arena.p, conc, c->counter(), c->dev, st, &c->launches);
+        break;
+    }
+    case 2: e = launch_decode(a, true, c->decode_lanes, c->counter(), c->dev, st, &c->launches); break;
+    default: e = launch_decode(a, false, c->decode_lanes, c->counter(), c->dev, st, &c->launches); break;
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+    return LZ4B200_OK;
+}
+
+// Host-memory batch: chunked, overlapped H2D / kernel / D2H.
+int run_host(lz4b200_ctx* c, const uint8_t* src, const int64_t* src_off, const int32_t* src_len,
+             uint8_t* dst, const int64_t* dst_off, const int32_t* dst_cap, int32_t* out_len, int32_t n, int op)
+{
+    const bool decode = op >= 2;
+    int32_t b0 = 0; int k = 0;
+    // Large chunks copy every maximal run of adjacent destination slots back in one transfer (bytes of a slot beyond
+    // the block's return value are unspecified, as with the reference's native codecs); small ones wait for the
+    // per-block results and copy exactly the produced bytes.
+    struct Pending { int32_t b0, b1; int64_t dlo; bool contiguous; int32_t* h_out; };
+    Pending pend[NSLOT]; bool busy[NSLOT] = {false, false, false};
+
+    auto retire = [&](int s) -> int {
+        // outputs of slot s are on the host once its event has fired; scatter out_len and (if needed) per-block payloads
+        if (!busy[s]) return LZ4B200_OK;
+        CU(cudaEventSynchronize(c->slot[s].done));
+        Pending& p = pend[s];
+        std::memcpy(out_len + p.b0, p.h_out, sizeof(int32_t) * (size_t)(p.b1 - p.b0));
+        if (!p.contiguous) {
+            // slots with gaps between them: copy exactly the bytes each block produced, nothing in between
+            for (int32_t i = p.b0; i < p.b1; i++) {
+                int32_t r = out_len[i];
+                int64_t nbytes = decode ? (op == 2 ? (r >= 0 ? dst_cap[i] : 0) : std::max(r, 0)) : std::max(r, 0);
+                if (nbytes > 0)
+                    CU(cudaMemcpyAsync(dst + dst_off[i], (uint8_t*)c->slot[s].dst.p + (dst_off[i] - p.dlo), (size_t)nbytes,
+                                       cudaMemcpyDeviceToHost, c->slot[s].stream));
+            }
+            CU(cudaStreamSynchronize(c->slot[s].stream));
+        }
+        busy[s] = false;
+        return LZ4B200_OK;
+    };
+
+    while (b0 < n) {
+        // ---- pick the chunk [b0, b1): bounded raw bytes ----
+        int64_t bytes = 0; int32_t b1 = b0;
+        while (b1 < n) {
+            int64_t w = std::max<int64_t>(src_len[b1], 0) + std::max<int64_t>(dst_cap[b1], 0);
+            if (b1 > b0 && bytes + w > (int64_t)HOST_CHUNK_BYTES) break;
+            bytes += w; b1++;
+        }
+        const int s = k % NSLOT; k++;
+        int rc = retire(s); if (rc) return rc;
+        Slot& sl = c->slot[s];
+        const int32_t m = b1 - b0;
+        int64_t slo = INT64_MAX, shi = INT64_MIN, dlo = INT64_MAX, dhi = INT64_MIN; bool contiguous = true;
+        for (int32_t i = b0; i < b1; i++) {
+            if (src_len[i] < 0 || dst_cap[i] < 0) return fail(LZ4B200_E_ARG, "negative block length");
+            slo = std::min(slo, src_off[i]); shi = std::max(shi, src_off[i] + src_len[i]);
+            dlo = std::min(dlo, dst_off[i]); dhi = std::max(dhi, dst_off[i] + dst_cap[i]);
+        }
+        contiguous = m > 8;
+        const size_t sbytes = (size_t)(shi - slo), dbytes = (size_t)(dhi - dlo);
+        CU(sl.src.reserve(sbytes + 64)); CU(sl.dst.reserve(dbytes + 64));
+        const size_t meta_bytes = (size_t)m * (8 + 4 + 8 + 4 + 4);
+        CU(sl.meta.reserve(meta_bytes)); CU(sl.hmeta.reserve(meta_bytes));
+        // meta layout: int64 src_off[m] | int64 dst_off[m] | int32 src_len[m] | int32 dst_cap[m] | int32 out_len[m]
+        int64_t* h_so = (int64_t*)sl.hmeta.p; int64_t* h_do = h_so + m;
+        int32_t* h_sl = (int32_t*)(h_do + m); int32_t* h_dc = h_sl + m; int32_t* h_out = h_dc + m;
+        for (int32_t i = 0; i < m; i++) {
+            h_so[i] = src_off[b0 + i] - slo; h_do[i] = dst_off[b0 + i] - dlo;
+            h_sl[i] = src_len[b0 + i]; h_dc[i] = dst_cap[b0 + i];
+        }
+        uint8_t* d_meta = (uint8_t*)sl.meta.p;
+        CU(cudaMemcpyAsync(d_meta, sl.hmeta.p, (size_t)m * 24, cudaMemcpyHostToDevice, sl.stream));
+        if (sbytes) CU(cudaMemcpyAsync(sl.src.p, src + slo, sbytes, cudaMemcpyHostToDevice, sl.stream));
+        BatchArgs a;
+        a.src = (const uint8_t*)sl.src.p; a.dst = (uint8_t*)sl.dst.p;
+        a.src_off = (const int64_t*)d_meta; a.dst_off = a.src_off + m;
+        a.src_len = (const int32_t*)(a.dst_off + m); a.dst_cap = a.src_len + m;
+        a.out_len = (int32_t*)(a.dst_cap + m); a.n_blocks = m;
+        rc = run_device(c, a, op, sl.stream); if (rc) return rc;
+        CU(cudaMemcpyAsync(h_out, a.out_len, sizeof(int32_t) * (size_t)m, cudaMemcpyDeviceToHost, sl.stream));
+        if (contiguous) {
+            int32_t r0 = b0;
+            for (int32_t i = b0 + 1; i <= b1; i++) {
+                if (i == b1 || dst_off[i] != dst_off[i - 1] + dst_cap[i - 1]) {
+                    const int64_t lo = dst_off[r0], hi = dst_off[i - 1] + dst_cap[i - 1];
+                    if (hi > lo) CU(cudaMemcpyAsync(dst + lo, (uint8_t*)sl.dst.p + (lo - dlo), (size_t)(hi - lo), cudaMemcpyDeviceToHost, sl.stream));
+                    r0 = i;
+                }
+            }
+        }
+        CU(cudaEventRecord(sl.done, sl.stream));
+        pend[s] = Pending{b0, b1, dlo, contiguous, h_out}; busy[s] = true;
+        b0 = b1;
+    }
+    for (int i = 0; i < NSLOT; i++) { int rc = retire((k + i) % NSLOT); if (rc) return rc; }
+    return LZ4B200_OK;
+}
+
+int batch(lz4b200_ctx* c, const void* src, const int64_t* src_off, const int32_t* src_len, void* dst,
+          const int64_t* dst_off, const int32_t* dst_cap, int32_t* out_len, int32_t n, int op, int mem, void* stream)
+{
+    if (!c) return fail(LZ4B200_E_ARG, "null context");
+    if (n < 0) return fail(LZ4B200_E_ARG, "negative block count");
+    if (n == 0) return LZ4B200_OK;
+    if (!src_off || !src_len || !dst_off || !dst_cap || !out_len || !src || !dst) return fail(LZ4B200_E_ARG, "null argument");
+    std::lock_guard<std::mutex> lock(c->mu);
+    DeviceGuard g(c->device);
+    if (!g.ok) return fail(LZ4B200_E_CUDA, "cudaSetDevice failed");
+    if (mem == LZ4B200_MEM_DEVICE) {
+        BatchArgs a{(const uint8_t*)src, src_off, src_len, (uint8_t*)dst, dst_off, dst_cap, out_len, n};
+        return run_device(c, a, op, stream ? (cudaStream_t)stream : c->stream);
+    }
+    if (mem != LZ4B200_MEM_HOST) return fail(LZ4B200_E_ARG, "mem must be LZ4B200_MEM_HOST or LZ4B200_MEM_DEVICE");
+    return run_host(c, (const uint8_t*)src, src_off, src_len, (uint8_t*)dst, dst_off, dst_cap, out_len, n, op);
+}
+
+std::mutex g_default_mu;
+lz4b200_ctx* g_default = nullptr;
+
+lz4b200_ctx* default_ctx()
+{
+    std::lock_guard<std::mutex> lock(g_default_mu);
+    if (!g_default) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+        if (lz4b200_create(&g_default, dev) != LZ4B200_OK) g_default = nullptr;
+    }
+    return g_default;
+}
+
+int single(const char* source, char* dest, int isize, int ocap, int op)
+{
+    lz4b200_ctx* c = default_ctx();
+    if (!c) return op >= 2 ? -1 : 0;               // no device: encoders report failure (0), decoders an error (<0)
+    if (!source || !dest || isize < 0 || ocap < 0) return op >= 2 ? -1 : 0;
+    int64_t so = 0, dof = 0; int32_t sl = isize, dc = ocap, out = op >= 2 ? -1 : 0;
+    // zero-length buffers still need valid pointers for the staging copies
+    int rc = batch(c, source, &so, &sl, dest, &dof, &dc, &out, 1, op, LZ4B200_MEM_HOST, nullptr);
+    if (rc != LZ4B200_OK) return op >= 2 ? -1 : 0;
+    return out;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lz4b200_version(void) { return LZ4B200_VERSION; }
+const char* lz4b200_last_error(void) { return g_err.c_str(); }
+
+int lz4b200_device_count(void)
+{
+    int n = 0, ok = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    for (int i = 0; i < n; i++) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, i) == cudaSuccess && major == 10) ok++;
+    }
+    return ok;
+}
+
+int lz4b200_compress_bound(int n) { return n < 0 ? 0 : n + n / 255 + 16; }
+
+int lz4b200_create(lz4b200_ctx** out, int device)
+{
+    if (!out) return fail(LZ4B200_E_ARG, "null out pointer");
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return fail(LZ4B200_E_NODEVICE, "no CUDA device"); }
+    if (device < 0 || device >= n) return fail(LZ4B200_E_ARG, "device index out of range");
+    int major = 0;
+    CU(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    if (major != 10) return fail(LZ4B200_E_NODEVICE, "device is not compute capability 10.x (this library holds sm_100a code only)");
+    DeviceGuard g(device);
+    if (!g.ok) return fail(LZ4B200_E_CUDA, "cudaSetDevice failed");
+    lz4b200_ctx* c = new lz4b200_ctx();
+    c->device = device;
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device); c->dev.num_sms = v;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device); c->dev.smem_per_sm = v;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device); c->dev.smem_optin = v;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&c->counters, sizeof(uint32_t) * NCOUNTER);
+    for (int i = 0; i < NSLOT && e == cudaSuccess; i++) {
+        e = cudaStreamCreateWithFlags(&c->slot[i].stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->slot[i].done, cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) { int rc = cuda_fail(e, "context creation"); lz4b200_destroy(c); return rc; }
+    *out = c;
+    return LZ4B200_OK;
+}
+
+void lz4b200_destroy(lz4b200_ctx* c)
+{
+    if (!c) return;
+    DeviceGuard g(c->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < NSLOT; i++) {
+        Slot& s = c->slot[i];
+        s.src.release(); s.dst.release(); s.meta.release(); s.hmeta.release();
+        if (s.done) cudaEventDestroy(s.done);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    c->hc_arena.release(); c->compact_tmp.release();
+    if (c->counters) cudaFree(c->counters);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int lz4b200_synchronize(lz4b200_ctx* c)
+{
+    if (!c) return fail(LZ4B200_E_ARG, "null context");
+    DeviceGuard g(c->device);
+    CU(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < NSLOT; i++) CU(cudaStreamSynchronize(c->slot[i].stream));
+    return LZ4B200_OK;
+}
+
+int lz4b200_encode_batch(lz4b200_ctx* c, const void* src, const int64_t* src_off, const int32_t* src_len, void* dst,
+                         const int64_t* dst_off, const int32_t* dst_cap, int32_t* out_len, int32_t n, int mode, int mem, void* stream)
+{
+    if (mode != LZ4B200_MODE_FAST && mode != LZ4B200_MODE_HC) return fail(LZ4B200_E_ARG, "unknown encoder mode");
+    return batch(c, src, src_off, src_len, dst, dst_off, dst_cap, out_len, n, mode == LZ4B200_MODE_HC ? 1 : 0, mem, stream);
+}
+
+int lz4b200_decode_batch(lz4b200_ctx* c, const void* src, const int64_t* src_off, const int32_t* src_len, void* dst,
+                         const int64_t* dst_off, const int32_t* dst_cap, int32_t* out_len, int32_t n, int known_len, int mem, void* stream)
+{
+    return batch(c, src, src_off, src_len, dst, dst_off, dst_cap, out_len, n, known_len ? 2 : 3, mem, stream);
+}
+
+int lz4b200_compact(lz4b200_ctx* c, const void* slots, const int64_t* slot_off, const int32_t* len, void* packed,
+                    int64_t* out_off, int32_t n, void* stream)
+{
+    if (!c || !slot_off || !len || !out_off || n < 0) return fail(LZ4B200_E_ARG, "bad argument");
+    std::lock_guard<std::mutex> lock(c->mu);
+    DeviceGuard g(c->device);
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    if (compact_tmp_bytes(n) > c->compact_tmp.cap) { CU(cudaDeviceSynchronize()); CU(c->compact_tmp.reserve(compact_tmp_bytes(n))); }
+    cudaError_t e = launch_compact((const uint8_t*)slots, slot_off, len, (uint8_t*)packed, out_off, n,
+                                   c->compact_tmp.p, c->compact_tmp.cap, c->dev, st, &c->launches);
+    if (e != cudaSuccess) return cuda_fail(e, "compact launch");
+    return LZ4B200_OK;
+}
+
+int lz4b200_synth_fill(lz4b200_ctx* c, void* dst, int64_t n_blocks, int32_t block_size, int cls, uint64_t seed,
+                       int64_t first_block, void* stream)
+{
+    if (!c || !dst) return fail(LZ4B200_E_ARG, "bad argument");
+    std::lock_guard<std::mutex> lock(c->mu);
+    DeviceGuard g(c->device);
+    cudaError_t e = launch_synth((uint8_t*)dst, n_blocks, block_size, cls, seed, first_block, c->dev,
+                                 stream ? (cudaStream_t)stream : c->stream, &c->launches);
+    if (e != cudaSuccess) return cuda_fail(e, "synth launch");
+    return LZ4B200_OK;
+}
+
+int lz4b200_set_option(lz4b200_ctx* c, const char* key, int64_t value)
+{
+    if (!c || !key) return fail(LZ4B200_E_ARG, "bad argument");
+    std::lock_guard<std::mutex> lock(c->mu);
+    std::string k(key);
+    if (k == "decode_lanes") { if (value != 8 && value != 16 && value != 32) return fail(LZ4B200_E_ARG, "decode_lanes must be 8, 16 or 32"); c->decode_lanes = (int)value; }
+    else if (k == "encode_ctas_per_sm") { if (value < 0 || value > 32) return fail(LZ4B200_E_ARG, "encode_ctas_per_sm out of range"); c->encode_ctas_per_sm = (int)value; }
+    else if (k == "hc_concurrency") {
+        if (value < 32 || value > (1 << 20)) return fail(LZ4B200_E_ARG, "hc_concurrency out of range");
+        DeviceGuard g(c->device);
+        cudaDeviceSynchronize();
+        c->hc_arena.release();
+        c->hc_concurrency = (int)value;
+    }
+    else return fail(LZ4B200_E_ARG, "unknown option");
+    return LZ4B200_OK;
+}
+
+int64_t lz4b200_launch_count(lz4b200_ctx* c) { return c ? c->launches : 0; }
+
+int lz4b200_compress_limitedOutput(const char* s, char* d, int isize, int cap) { return single(s, d, isize, cap, 0); }
+int lz4b200_compressHC_limitedOutput(const char* s, char* d, int isize, int cap) { return single(s, d, isize, cap, 1); }
+int lz4b200_uncompress(const char* s, char* d, int isize, int osize) { return single(s, d, isize, osize, 2); }
+int lz4b200_uncompress_unknownOutputSize(const char* s, char* d, int isize, int cap) { return single(s, d, isize, cap, 3); }
+
+}  // extern "C"

@@ -1,0 +1,85 @@
+// encode.cu -- kernels + launchers for the fast and the HC encoders.
+#include "kernels.h"
+#include "lz4_encode.cuh"
+#include "lz4hc_encode.cuh"
+
+namespace lz4b200 {
+
+// ---- fast encoder: one warp (= one CTA) per block, persistent, dynamic block hand-out --------------------------------
+// The position table is dynamic shared memory so the launcher can also use its size to pin the number of CTAs per SM.
+__global__ void __launch_bounds__(32)
+lz4_encode_fast_kernel(BatchArgs a, uint32_t* counter)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    EncShared* sh = (EncShared*)smem;
+    const int lane = threadIdx.x;
+    for (;;) {
+        uint32_t b = 0;
+        if (lane == 0) b = atomicAdd(counter, 1u);
+        b = simt::shfl(0xFFFFFFFFu, b, 0);
+        if (b >= (uint32_t)a.n_blocks) break;
+        const int r = encode_block(sh, a.src + a.src_off[b], a.src_len[b], a.dst + a.dst_off[b], a.dst_cap[b], lane);
+        if (lane == 0) a.out_len[b] = r;
+    }
+}
+
+cudaError_t launch_encode_fast(const BatchArgs& a, uint32_t* counter, int ctas_per_sm,
+                               const DeviceInfo& dev, cudaStream_t stream, int64_t* launches)
+{
+    if (a.n_blocks <= 0) return cudaSuccess;
+    // each CTA costs its dynamic bytes + 1 KiB of system-reserved shared memory
+    const int max_ctas = dev.smem_per_sm / ((int)sizeof(EncShared) + 1024);
+    if (ctas_per_sm < 1 || ctas_per_sm > max_ctas) ctas_per_sm = max_ctas;
+    if (ctas_per_sm > 32) ctas_per_sm = 32;
+    int dyn = dev.smem_per_sm / ctas_per_sm - 1024;
+    dyn &= ~1023;
+    if (dyn > dev.smem_optin) dyn = dev.smem_optin & ~1023;
+    if (dyn < (int)sizeof(EncShared)) dyn = (int)sizeof(EncShared);
+    cudaError_t e = cudaFuncSetAttribute(lz4_encode_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), stream);
+    if (e != cudaSuccess) return e;
+    long long grid = (long long)dev.num_sms * ctas_per_sm;
+    if (grid > a.n_blocks) grid = a.n_blocks;
+    lz4_encode_fast_kernel<<<(unsigned)grid, 32, dyn, stream>>>(a, counter);
+    if (launches) ++*launches;
+    return cudaGetLastError();
+}
+
+// ---- HC encoder: one THREAD per block, state arena in global memory -------------------------------------------------
+constexpr int HC_THREADS = 32;
+
+__global__ void __launch_bounds__(HC_THREADS)
+lz4_encode_hc_kernel(BatchArgs a, uint8_t* arena, uint32_t* counter)
+{
+    const size_t slot = (size_t)blockIdx.x * HC_THREADS + threadIdx.x;
+    void* state = arena + slot * HC_STATE_BYTES;
+    for (;;) {
+        const uint32_t b = atomicAdd(counter, 1u);
+        if (b >= (uint32_t)a.n_blocks) break;
+        a.out_len[b] = hc_encode_block(state, a.src + a.src_off[b], a.src_len[b], a.dst + a.dst_off[b], a.dst_cap[b]);
+    }
+}
+
+size_t hc_scratch_bytes(int concurrency)
+{
+    size_t slots = ((size_t)concurrency + HC_THREADS - 1) / HC_THREADS * HC_THREADS;
+    return slots * HC_STATE_BYTES;
+}
+
+cudaError_t launch_encode_hc(const BatchArgs& a, void* scratch, int concurrency, uint32_t* counter,
+                             const DeviceInfo&, cudaStream_t stream, int64_t* launches)
+{
+    if (a.n_blocks <= 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), stream);
+    if (e != cudaSuccess) return e;
+    long long ctas = ((long long)concurrency + HC_THREADS - 1) / HC_THREADS;
+    long long want = ((long long)a.n_blocks + HC_THREADS - 1) / HC_THREADS;
+    if (ctas > want) ctas = want;
+    if (ctas < 1) ctas = 1;
+    lz4_encode_hc_kernel<<<(unsigned)ctas, HC_THREADS, 0, stream>>>(a, (uint8_t*)scratch, counter);
+    if (launches) ++*launches;
+    return cudaGetLastError();
+}
+
+}  // namespace lz4b200

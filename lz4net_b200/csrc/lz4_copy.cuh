@@ -30,6 +30,16 @@ SIMT_DEV uint4 shift16(uint4 lo, uint4 hi, uint32_t r)
     return o;
 }
 
+// little-endian 32-bit read at an arbitrary byte position of the (read-only) input
+SIMT_DEV uint32_t in32(const uint8_t* src, int p)
+{
+    const uint8_t* a = (const uint8_t*)((uintptr_t)(src + p) & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)((uintptr_t)(src + p) & 3) * 8;
+    const uint32_t lo = simt::ldg_nc_u32(a);
+    const uint32_t hi = sh ? simt::ldg_nc_u32(a + 4) : 0u;           // (never touches a word holding no wanted byte)
+    return simt::funnel_r(lo, hi, sh);
+}
+
 // ---- source policies -------------------------------------------------------------------------------------------
 // Ring in shared memory: byte i of the source lives at buf[(pos0 + i) & (SIZE-1)].
 template <int SIZE>

@@ -26,16 +26,6 @@ struct alignas(16) EncShared { uint32_t table[4096]; };
 
 constexpr int LZ4_64KLIMIT = 65547;                                // original/lz4.c:565
 
-// little-endian 32-bit read at an arbitrary byte position of the (read-only) input
-SIMT_DEV uint32_t in32(const uint8_t* src, int p)
-{
-    const uint8_t* a = (const uint8_t*)((uintptr_t)(src + p) & ~(uintptr_t)3);
-    const uint32_t sh = (uint32_t)((uintptr_t)(src + p) & 3) * 8;
-    const uint32_t lo = simt::ldg_nc_u32(a);
-    const uint32_t hi = sh ? simt::ldg_nc_u32(a + 4) : 0u;           // (never touches a word holding no wanted byte)
-    return simt::funnel_r(lo, hi, sh);
-}
-
 // token length extension: `v` as a run of 255s plus a remainder byte, written lane-parallel; returns bytes written
 SIMT_DEV int put_len_ext(uint8_t* dst, int op, int cap, int v, int lane)
 {

@@ -87,3 +87,15 @@ def encode(blocks, caps=None, sched_seed=1, src_skew=0, dst_skew=0):
         assert (d[:lo] == 0xCD).all() and (d[lo + max(c, 0):] == 0xCD).all(), "encoder wrote outside [dst, dst+cap)"
         outs.append(d[lo:lo + max(r, 0)].tobytes())
     return res.tolist(), outs
+
+
+def encode_hc(block, cap=None, src_skew=0):
+    n = len(block)
+    if cap is None:
+        cap = n + n // 255 + 16
+    a = np.zeros(src_skew + n + 64, np.uint8)
+    a[src_skew:src_skew + n] = np.frombuffer(block, np.uint8)
+    d = np.full(max(cap, 0) + 96, 0xCD, np.uint8)
+    r = lib().emu_encode_hc(C.c_void_p(a.ctypes.data + src_skew), n, C.c_void_p(d.ctypes.data + 32), cap)
+    assert (d[:32] == 0xCD).all() and (d[32 + max(cap, 0):] == 0xCD).all(), "HC encoder wrote outside [dst, dst+cap)"
+    return int(r), d[32:32 + max(r, 0)].tobytes()

@@ -4,6 +4,7 @@
 #include "simt_emu.h"
 #include "lz4_decode.cuh"
 #include "lz4_encode.cuh"
+#include "lz4hc_encode.cuh"
 #include <stdlib.h>
 #include <vector>
 
@@ -68,6 +69,16 @@ void emu_decode(int G, int known, int nblocks, const uint8_t* const* src, const 
     j->G = G; j->known = known != 0; j->nblocks = nblocks; j->src = src; j->isize = isize; j->dst = dst; j->cap = cap; j->result = result;
     simt_emu::run_warp(dec_entry, j, sched_seed);
     delete j;
+}
+
+// the HC encoder is one thread per block: plain scalar code, no warp needed
+int emu_encode_hc(const uint8_t* src, int n, uint8_t* dst, int cap)
+{
+    void* st = aligned_alloc(16, HC_STATE_BYTES);
+    memset(st, 0x5A, HC_STATE_BYTES);               // stale garbage, like a reused arena slot
+    int r = hc_encode_block(st, src, n, dst, cap);
+    free(st);
+    return r;
 }
 
 void emu_encode(int nblocks, const uint8_t* const* src, const int* n, uint8_t* const* dst, const int* cap,

@@ -1,0 +1,325 @@
+"""GPU parity tests (B200): every check calls liblz4b200.so through its C ABI and compares with the oracle.
+
+Same shape as lz4net's ConformanceTests (src/LZ4.Tests/ConformanceTests.cs:57-148: all encoders byte-identical, all
+decoders round-trip), WrapTests.cs:11-48, StreamTests.cs:22-63 and the upstream fuzzer's +-1 invariants
+(original/fuzzer.c:176-227), with the synthetic content models of tests/cases.py instead of the Silesia corpus."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import lz4net_b200
+    return lz4net_b200.default_context()
+
+
+def _inputs(models=cases.MODELS, lens=None, seed0=0):
+    lens = lens or ([65536] + cases.random_lengths(6, 65546, seed=77) + [65546, 13, 12, 1, 0, 300])
+    out = []
+    for i, m in enumerate(models):
+        for j, n in enumerate(lens):
+            out.append(cases.content(m, n, seed=seed0 + 31 * i + j).tobytes())
+    return out
+
+
+def test_library_loaded_and_device_present():
+    from lz4net_b200 import native
+    assert native.lib().lz4b200_device_count() >= 1
+
+
+def test_encode_fast_byte_identical(ctx):
+    blocks = _inputs()
+    res, outs = ctx.encode_blocks(blocks)
+    for b, r, o in zip(blocks, res, outs):
+        assert (r, o) == oracle.encode(b), len(b)
+
+
+def test_encode_hc_byte_identical(ctx):
+    blocks = _inputs(lens=[65536, 40000, 65546, 20, 12, 0, 100000])
+    res, outs = ctx.encode_blocks(blocks, hc=True)
+    for b, r, o in zip(blocks, res, outs):
+        assert (r, o) == oracle.encode_hc(b), len(b)
+
+
+def test_encode_general_variant_above_64k(ctx):
+    blocks = [cases.content(m, n, seed=7).tobytes()
+              for m, n in (("ETEXT", 65547), ("lowent", 70001), ("E50", 150000), ("periodic", 1 << 20), ("mixed", 69999),
+                           ("E100", 200000), ("runs", 131072), ("E0", 66000), ("ETEXT", 1 << 20))]
+    res, outs = ctx.encode_blocks(blocks)
+    for b, r, o in zip(blocks, res, outs):
+        assert (r, o) == oracle.encode(b), len(b)
+
+
+@pytest.mark.parametrize("hc", [False, True])
+def test_encode_limited_output(ctx, hc):
+    """cap = exact / one short / n (LZ4Stream.cs:243-246, LZ4Codec.cs:518-523) / tiny -- same verdict and bytes."""
+    fn = oracle.encode_hc if hc else oracle.encode
+    blocks, caps = [], []
+    for i, m in enumerate(cases.MODELS):
+        for n in (200, 3000, 65536):
+            d = cases.content(m, n, seed=40 + i).tobytes()
+            r = fn(d)[0]
+            for cap in (r, r - 1, n, n - 1, r // 2, 0, 1, 7, 8, 13):
+                if cap >= 0:
+                    blocks.append(d); caps.append(cap)
+    res, outs = ctx.encode_blocks(blocks, caps=caps, hc=hc)
+    for b, c, r, o in zip(blocks, caps, res, outs):
+        assert (r, o) == fn(b, cap=c), (len(b), c)
+
+
+def test_golden_vectors(ctx):
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden_v1.json")))
+    datas = [cases.AUTOTEST if c["model"] == "autotest" else cases.content(c["model"], c["n"], c["seed"]).tobytes() for c in g["cases"]]
+    for mode, hc in (("fast", False), ("hc", True)):
+        res, outs = ctx.encode_blocks(datas, hc=hc)
+        res2, _ = ctx.encode_blocks(datas, caps=[len(d) for d in datas], hc=hc)
+        for c, r, o, r2 in zip(g["cases"], res, outs, res2):
+            assert r == c[mode]["len"] and hashlib.sha256(o).hexdigest() == c[mode]["sha256"], (c["name"], mode)
+            assert r2 == c[mode]["len_cap_n"], (c["name"], mode)
+
+
+@pytest.mark.parametrize("lanes", [32, 16, 8])
+@pytest.mark.parametrize("known", [True, False])
+def test_decode_bit_exact(ctx, lanes, known):
+    ctx.set_option("decode_lanes", lanes)
+    raws = _inputs(lens=[65536, 1, 12, 13, 700, 33000, 200000])
+    comp = []
+    for i, d in enumerate(raws):
+        comp.append((oracle.encode_hc if i % 3 == 0 else oracle.encode)(d)[1])
+    res, outs = ctx.decode_blocks(comp, [len(d) for d in raws], known=known)
+    ctx.set_option("decode_lanes", 32)
+    for c, d, r, o in zip(comp, raws, res, outs):
+        assert r == (len(c) if known else len(d)), (len(d), r)
+        assert o == d
+
+
+def test_decode_size_invariants(ctx):
+    """original/fuzzer.c:176-210: exact size works, size +-1 must fail; verdicts equal the oracle's."""
+    from lz4net_b200 import synth
+    for known in (True, False):
+        comp, caps, expect = [], [], []
+        for seed in range(8):
+            d = synth.fuz_block(seed, 8000).tobytes()
+            c = oracle.encode(d)[1]
+            n = len(d)
+            if known:
+                for osz in (n, n - 1, n + 1):
+                    comp.append(c); caps.append(osz); expect.append(oracle.decode_known(c, osz)[0])
+            else:
+                for cc, osz in ((c, n + 1), (c, n), (c, n - 1), (c[:-1], n), (c + b"\0", n)):
+                    comp.append(cc); caps.append(osz); expect.append(oracle.decode_unknown(cc, osz)[0])
+        res, _ = ctx.decode_blocks(comp, caps, known=known)
+        for r, e in zip(res, expect):
+            assert (r < 0) == (e < 0) and (e < 0 or r == e), (r, e)
+        assert any(e < 0 for e in expect) and any(e >= 0 for e in expect)
+
+
+@pytest.mark.parametrize("known", [True, False])
+def test_decode_corrupt_streams(ctx, known):
+    rng = np.random.default_rng(5)
+    comp, caps = [], []
+    for i in range(400):
+        d = cases.content("mixed", 2500, seed=i).tobytes()
+        c = bytearray(oracle.encode(d)[1])
+        kind = i % 3
+        if kind == 0:
+            for _ in range(int(rng.integers(1, 4))):
+                c[int(rng.integers(0, len(c)))] ^= 1 << int(rng.integers(0, 8))
+        elif kind == 1:
+            c = c[: int(rng.integers(1, len(c)))]
+        else:
+            c[int(rng.integers(0, len(c)))] = 0xFF
+        comp.append(bytes(c)); caps.append(len(d))
+    res, outs = ctx.decode_blocks(comp, caps, known=known)
+    for c, cap, r, o in zip(comp, caps, res, outs):
+        er, eo = (oracle.decode_known if known else oracle.decode_unknown)(c, cap)
+        assert (r < 0) == (er < 0), (r, er)
+        if er >= 0:
+            assert r == er and o[:len(eo)] == eo
+
+
+def test_decode_length_overflow_input(ctx):
+    """original/fuzzer.c:96-116 (issue 52): 0x0F 00 00 then 0xFF... must be rejected, not overflow."""
+    bad = bytes([0x0F, 0, 0]) + b"\xff" * (1 << 20)
+    res, _ = ctx.decode_blocks([bad], [1 << 20], known=True)
+    assert res[0] < 0
+    res, _ = ctx.decode_blocks([bad], [1 << 20], known=False)
+    assert res[0] < 0
+
+
+def test_synth_device_equals_numpy(ctx):
+    import torch
+    from lz4net_b200 import batch, synth
+    for cid, cls in enumerate(synth.CLASSES):
+        for bs, nb, first in ((65536, 5, 0), (1000, 7, 123456), (65536 + 13, 3, 9)):
+            t = torch.empty(nb * bs, dtype=torch.uint8, device="cuda")
+            batch.synth_fill(ctx, t, nb, bs, cid, seed=42, first_block=first)
+            torch.cuda.synchronize()
+            want = synth.make_blocks(cls, nb, bs, seed=42, first_block=first)
+            assert np.array_equal(t.cpu().numpy().reshape(nb, bs), want), (cls, bs)
+
+
+@pytest.mark.parametrize("cls", ["E0", "E50", "E100", "ETEXT"])
+def test_device_batch_roundtrip_and_sampled_parity(ctx, cls):
+    """BASELINE config 2 shape at a size that runs in seconds: device-resident batch, encode -> compact -> decode,
+    whole-batch equality on the device, byte parity with the oracle on a sample of blocks."""
+    import torch
+    from lz4net_b200 import batch, synth
+    nb, bs = 4096, 65536
+    slot = oracle.bound(bs)
+    raw = torch.empty(nb * bs, dtype=torch.uint8, device="cuda")
+    batch.synth_fill(ctx, raw, nb, bs, synth.CLASS_ID[cls], seed=3)
+    so, do, sl, dc = batch.uniform_layout(nb, bs, slot, "cuda")
+    slots = torch.empty(nb * slot, dtype=torch.uint8, device="cuda")
+    clen = torch.zeros(nb, dtype=torch.int32, device="cuda")
+    batch.encode(ctx, raw, so, sl, slots, do, dc, clen)
+    off = torch.zeros(nb + 1, dtype=torch.int64, device="cuda")
+    packed = torch.empty(nb * slot, dtype=torch.uint8, device="cuda")
+    batch.compact(ctx, slots, do, clen, packed, off)
+    out = torch.zeros(nb * bs, dtype=torch.uint8, device="cuda")
+    consumed = torch.zeros(nb, dtype=torch.int32, device="cuda")
+    batch.decode(ctx, packed, off[:-1].contiguous(), clen, out, so, sl, consumed, known=True)
+    torch.cuda.synchronize()
+    assert torch.equal(off[1:] - off[:-1], clen.to(torch.int64))
+    assert torch.equal(consumed, clen)
+    assert torch.equal(out, raw)
+    h_raw = raw.cpu().numpy().reshape(nb, bs); h_len = clen.cpu().numpy(); h_off = off.cpu().numpy(); h_packed = packed.cpu().numpy()
+    for i in list(range(0, nb, 257)) + [nb - 1]:
+        r, o = oracle.encode(h_raw[i])
+        assert h_len[i] == r and h_packed[h_off[i]:h_off[i] + r].tobytes() == o, i
+
+
+def test_device_batch_hc_sampled_parity(ctx):
+    import torch
+    from lz4net_b200 import batch, synth
+    nb, bs = 1024, 65536
+    slot = oracle.bound(bs)
+    raw = torch.empty(nb * bs, dtype=torch.uint8, device="cuda")
+    q = nb // 4
+    for cid in range(4):
+        batch.synth_fill(ctx, raw[cid * q * bs:], q, bs, cid, seed=5, first_block=cid * q)
+    so, do, sl, dc = batch.uniform_layout(nb, bs, slot, "cuda")
+    slots = torch.empty(nb * slot, dtype=torch.uint8, device="cuda")
+    clen = torch.zeros(nb, dtype=torch.int32, device="cuda")
+    batch.encode(ctx, raw, so, sl, slots, do, dc, clen, hc=True)
+    out = torch.zeros(nb * bs, dtype=torch.uint8, device="cuda")
+    consumed = torch.zeros(nb, dtype=torch.int32, device="cuda")
+    batch.decode(ctx, slots, do, clen, out, so, sl, consumed, known=True)
+    torch.cuda.synchronize()
+    assert torch.equal(out, raw) and torch.equal(consumed, clen)
+    h_raw = raw.cpu().numpy().reshape(nb, bs); h_len = clen.cpu().numpy(); h_slots = slots.cpu().numpy().reshape(nb, slot)
+    for i in range(0, nb, 61):
+        r, o = oracle.encode_hc(h_raw[i])
+        assert h_len[i] == r and h_slots[i, :r].tobytes() == o, i
+
+
+def test_single_block_entry_points_and_autotest(ctx):
+    """The startup self-test every lz4net service must pass (src/LZ4/LZ4Codec.cs:173-239), via the LZ4Codec mirror."""
+    from lz4net_b200 import LZ4Codec
+    original = bytearray(cases.AUTOTEST)
+    for enc, oracle_enc in ((LZ4Codec.Encode, oracle.encode), (LZ4Codec.EncodeHC, oracle.encode_hc)):
+        encoded = bytearray(LZ4Codec.MaximumOutputLength(len(original)))
+        n = enc(original, 0, len(original), encoded, 0, len(encoded))
+        assert (n, bytes(encoded[:n])) == oracle_enc(bytes(original))
+        decoded = bytearray(len(original))
+        assert LZ4Codec.Decode(encoded, 0, n, decoded, 0, len(decoded), True) == len(original) and decoded == original
+        decoded = bytearray(len(original))
+        assert LZ4Codec.Decode(encoded, 0, n, decoded, 0, len(decoded), False) == len(original) and decoded == original
+        with pytest.raises(ValueError):
+            LZ4Codec.Decode(encoded, 0, n - 1, bytearray(len(original)), 0, len(original), True)
+    assert LZ4Codec.Encode(bytearray(0), 0, 0, bytearray(16), 0, 16) == 0          # C# boundary: empty input -> 0
+    assert LZ4Codec.Encode(bytes(original)) == oracle.encode(bytes(original))[1]
+    assert LZ4Codec.Decode(LZ4Codec.EncodeHC(bytes(original)), 0, -1, len(original)) == bytes(original)
+    # incompressible input with cap = n: fast -> 0, HC -> -1 (src/LZ4ps/LZ4Codec.Safe.cs:721-723)
+    rnd = bytearray(cases.content("E0", 2048, 1).tobytes())
+    assert LZ4Codec.Encode(rnd, 0, 2048, bytearray(2048), 0, 2048) == 0
+    assert LZ4Codec.EncodeHC(rnd, 0, 2048, bytearray(2048), 0, 2048) == -1
+
+
+def test_wrap_unwrap(ctx):
+    """src/LZ4.Tests/WrapTests.cs:11-48: lorem, incompressible 2 KiB (stored), one-byte inputs; fast and HC."""
+    from lz4net_b200 import LZ4Codec
+
+    def ref_wrap(d, hc):
+        if not d:
+            return bytes(8)
+        r, o = (oracle.encode_hc if hc else oracle.encode)(d, cap=len(d))
+        if r >= len(d) or r <= 0:
+            return len(d).to_bytes(4, "little") * 2 + d
+        return len(d).to_bytes(4, "little") + r.to_bytes(4, "little") + o
+
+    for d in (cases.LOREM, cases.content("E0", 2048, 0).tobytes(), b"a", b"", cases.AUTOTEST, cases.content("ETEXT", 70000, 1).tobytes()):
+        for hc, fn in ((False, LZ4Codec.Wrap), (True, LZ4Codec.WrapHC)):
+            w = fn(d)
+            assert w == ref_wrap(d, hc)
+            assert LZ4Codec.Unwrap(w) == d
+    with pytest.raises(ValueError):
+        LZ4Codec.Unwrap(b"\x01\x02\x03")
+
+
+def _ref_stream(data, block_size, hc):
+    """The LZ4Stream wire bytes, built from the oracle (src/LZ4/LZ4Stream.cs:225-269)."""
+    def varint(v):
+        out = bytearray()
+        while True:
+            b = v & 0x7F; v >>= 7
+            out.append(b | (0x80 if v else 0))
+            if not v:
+                return bytes(out)
+    out = bytearray()
+    for o in range(0, len(data), block_size):
+        blk = data[o:o + block_size]
+        r, c = (oracle.encode_hc if hc else oracle.encode)(blk, cap=len(blk))
+        comp = 0 < r < len(blk)
+        out += varint((1 if comp else 0) | (2 if hc else 0)) + varint(len(blk))
+        if comp:
+            out += varint(r)
+        out += c if comp else blk
+    return bytes(out)
+
+
+@pytest.mark.parametrize("hc", [False, True])
+def test_lz4stream_wire_format(ctx, hc):
+    """StreamTests.cs:22-63 shape: write, read back; plus byte equality of the chunk stream with the reference format."""
+    data = b"".join(cases.content(m, n, seed=9).tobytes() for m, n in
+                    (("ETEXT", 200000), ("E0", 70000), ("E100", 130000), ("mixed", 65536), ("lowent", 12345)))
+    for bs in (65536, 1 << 20, 1000, 16):
+        d = data if bs >= 1000 else data[:3000]
+        s = ctx.stream_encode(d, bs, hc)
+        assert s == _ref_stream(d, bs, hc), bs
+        assert ctx.stream_decode(s) == d
+    assert ctx.stream_encode(b"", 65536, hc) == b"" and ctx.stream_decode(b"") == b""
+    s = ctx.stream_encode(data[:100000], 65536, hc)
+    with pytest.raises((EOFError, ValueError)):
+        ctx.stream_decode(s[:-1])
+
+
+def test_compact_scan(ctx):
+    import torch
+    from lz4net_b200 import batch
+    rng = np.random.default_rng(1)
+    for n in (1, 7, 1024, 1025, 5000, 300000):
+        lens = rng.integers(-2, 700, n).astype(np.int32)
+        slot = 704
+        slots = torch.randint(0, 256, (n * slot,), dtype=torch.uint8, device="cuda")
+        so = torch.arange(n, dtype=torch.int64, device="cuda") * slot
+        tl = torch.from_numpy(lens).cuda()
+        off = torch.zeros(n + 1, dtype=torch.int64, device="cuda")
+        packed = torch.zeros(int(np.maximum(lens, 0).sum()) + 16, dtype=torch.uint8, device="cuda")
+        batch.compact(ctx, slots, so, tl, packed, off)
+        torch.cuda.synchronize()
+        want = np.concatenate([[0], np.cumsum(np.maximum(lens, 0), dtype=np.int64)])
+        assert np.array_equal(off.cpu().numpy(), want)
+        hs = slots.cpu().numpy().reshape(n, slot); hp = packed.cpu().numpy()
+        for i in list(range(0, n, max(1, n // 50))):
+            l = max(int(lens[i]), 0)
+            assert np.array_equal(hp[want[i]:want[i] + l], hs[i, :l])
