@@ -6,7 +6,7 @@
  * original/lz4hc.h:57); a `CudaLZ4Service : ILZ4Service` (src/LZ4/ILZ4Service.cs:30-36) binds the entry points
  * below with [DllImport] exactly like CppMM64LZ4Service (src/LZ4/Services/CppMM64LZ4Service.cs:38-51) binds those.
  * INTEGRATION.md shows the managed stub.  Plain pointers and sizes only; no torch / CUDA types in any signature
- * (a `void* stream` is a cudaStream_t passed opaquely; NULL = the context's own stream).
+ * (a `void* stream` is a cudaStream_t passed opaquely; NULL = the CUDA default stream, as everywhere in CUDA).
  *
  * Conventions shared with the reference:
  *   - encoders return bytes written, 0 = output too small / failed              (original/lz4.h:48-60)

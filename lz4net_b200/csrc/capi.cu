@@ -78,7 +78,7 @@ struct lz4b200_ctx {
     uint32_t* counters = nullptr;
     int next_counter = 0;
     DevBuf hc_arena, compact_tmp;
-    int decode_lanes = 32;
+    int decode_lanes = 16;
     int encode_ctas_per_sm = 0;            // 0 = as many as shared memory allows
     int hc_concurrency = 16384;
     Slot slot[NSLOT];
@@ -221,7 +221,7 @@ int batch(lz4b200_ctx* c, const void* src, const int64_t* src_off, const int32_t
     if (!g.ok) return fail(LZ4B200_E_CUDA, "cudaSetDevice failed");
     if (mem == LZ4B200_MEM_DEVICE) {
         BatchArgs a{(const uint8_t*)src, src_off, src_len, (uint8_t*)dst, dst_off, dst_cap, out_len, n};
-        return run_device(c, a, op, stream ? (cudaStream_t)stream : c->stream);
+        return run_device(c, a, op, (cudaStream_t)stream);
     }
     if (mem != LZ4B200_MEM_HOST) return fail(LZ4B200_E_ARG, "mem must be LZ4B200_MEM_HOST or LZ4B200_MEM_DEVICE");
     return run_host(c, (const uint8_t*)src, src_off, src_len, (uint8_t*)dst, dst_off, dst_cap, out_len, n, op);
@@ -347,7 +347,7 @@ int lz4b200_compact(lz4b200_ctx* c, const void* slots, const int64_t* slot_off, 
     if (!c || !slot_off || !len || !out_off || n < 0) return fail(LZ4B200_E_ARG, "bad argument");
     std::lock_guard<std::mutex> lock(c->mu);
     DeviceGuard g(c->device);
-    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    cudaStream_t st = (cudaStream_t)stream;
     if (compact_tmp_bytes(n) > c->compact_tmp.cap) { CU(cudaDeviceSynchronize()); CU(c->compact_tmp.reserve(compact_tmp_bytes(n))); }
     cudaError_t e = launch_compact((const uint8_t*)slots, slot_off, len, (uint8_t*)packed, out_off, n,
                                    c->compact_tmp.p, c->compact_tmp.cap, c->dev, st, &c->launches);
@@ -362,7 +362,7 @@ int lz4b200_synth_fill(lz4b200_ctx* c, void* dst, int64_t n_blocks, int32_t bloc
     std::lock_guard<std::mutex> lock(c->mu);
     DeviceGuard g(c->device);
     cudaError_t e = launch_synth((uint8_t*)dst, n_blocks, block_size, cls, seed, first_block, c->dev,
-                                 stream ? (cudaStream_t)stream : c->stream, &c->launches);
+                                 (cudaStream_t)stream, &c->launches);
     if (e != cudaSuccess) return cuda_fail(e, "synth launch");
     return LZ4B200_OK;
 }

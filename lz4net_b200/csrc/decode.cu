@@ -5,14 +5,17 @@
 namespace lz4b200 {
 
 constexpr int DEC_THREADS = 128;
+// registers: a cap of 40 (12 CTAs/SM) spills the loop state of the sub-warp variants to local memory (measured:
+// 2 LDL per sequence, half of them L1 misses) -- leave the compiler its ~56 registers, 9 CTAs = 36 warps per SM.
+constexpr int DEC_MIN_CTAS = 9;
 
 // Persistent CTAs; each group of G lanes pulls the next block index from a global counter.
 template <int G, bool KNOWN>
-__global__ void __launch_bounds__(DEC_THREADS)
+__global__ void __launch_bounds__(DEC_THREADS, DEC_MIN_CTAS)
 lz4_decode_kernel(BatchArgs a, uint32_t* counter)
 {
     constexpr int GROUPS = DEC_THREADS / G;
-    __shared__ DecRing rings[GROUPS];
+    __shared__ DecRing<G> rings[GROUPS];
     const int grp = threadIdx.x / G;
     const int wl = threadIdx.x & 31;                               // lane within the warp
     const int leader = wl & ~(G - 1);
@@ -20,7 +23,7 @@ lz4_decode_kernel(BatchArgs a, uint32_t* counter)
 
     DecStream<G> st;
     st.ring = &rings[grp]; st.lane = wl - leader; st.gmask = gmask;
-    for (int s = 0; s < DEC_SLOTS; s++) st.uses[s] = 0;
+    st.gbase = 0;
     if (st.lane == 0) {
         for (int s = 0; s < DEC_SLOTS; s++) simt::mbar_init(&st.ring->bar[s], 1);
         simt::fence_mbar_init();

@@ -26,27 +26,12 @@ SIMT_DEV int clz(uint32_t v) { return __clz((int)v); }
 SIMT_DEV int popc(uint32_t v) { return __popc(v); }
 SIMT_DEV uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) { return __funnelshift_r(lo, hi, sh); }
 
-// coherent loads (data this kernel wrote earlier: decoder back-references)
-// (plain ld.global -- L1-cacheable; the asm "memory" clobber only stops the compiler from hoisting it over the
-//  __syncwarp() that orders it after another lane's store)
-SIMT_DEV uint8_t  ldg_u8(const uint8_t* p)
-{
-    uint32_t r;
-    asm volatile("ld.global.u8 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
-    return (uint8_t)r;
-}
-SIMT_DEV uint32_t ldg_u32(const void* p)
-{
-    uint32_t r;
-    asm volatile("ld.global.u32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
-    return r;
-}
-SIMT_DEV uint4    ldg_v4(const void* p)
-{
-    uint4 r;
-    asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
-    return r;
-}
+// coherent loads (data this kernel wrote earlier: decoder back-references): plain ld.global, L1-cacheable.  They are
+// always separated from the producing store of another lane by a __syncwarp(), which is a memory barrier for the
+// compiler as well, so no asm/volatile is needed (and plain loads can be predicated instead of branched around).
+SIMT_DEV uint8_t  ldg_u8(const uint8_t* p) { return *p; }
+SIMT_DEV uint32_t ldg_u32(const void* p) { return *(const uint32_t*)p; }
+SIMT_DEV uint4    ldg_v4(const void* p) { return *(const uint4*)p; }
 // read-only path (kernel inputs)
 SIMT_DEV uint8_t  ldg_nc_u8(const uint8_t* p) { return __ldg(p); }
 SIMT_DEV uint32_t ldg_nc_u32(const void* p) { return __ldg((const uint32_t*)p); }
@@ -69,13 +54,16 @@ SIMT_DEV void fence_mbar_init()
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
-// one thread: arm the barrier with the byte count, then launch the copy that will complete_tx on it
-SIMT_DEV void bulk_g2s(void* sdst, const void* gsrc, uint32_t bytes, mbar_t* b)
+// one thread: arm the barrier phase with the total byte count of the copies that will complete_tx on it ...
+SIMT_DEV void mbar_expect(mbar_t* b, uint32_t bytes)
 {
-    uint32_t bar = smem_u32(b);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+// ... then launch them (bytes: multiple of 16; both addresses 16 B aligned)
+SIMT_DEV void bulk_copy(void* sdst, const void* gsrc, uint32_t bytes, mbar_t* b)
+{
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
+                 :: "r"(smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(b)) : "memory");
 }
 SIMT_DEV void mbar_wait(mbar_t* b, uint32_t parity)
 {

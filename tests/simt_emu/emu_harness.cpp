@@ -15,8 +15,12 @@ namespace {
 struct DecJob {
     int G; bool known; int nblocks;
     const uint8_t* const* src; const int* isize; uint8_t* const* dst; const int* cap; int* result;
-    DecRing rings[4];
+    DecRing<32> r32[1]; DecRing<16> r16[2]; DecRing<8> r8[4];
+    template <int G> DecRing<G>* rings();
 };
+template <> DecRing<32>* DecJob::rings<32>() { return r32; }
+template <> DecRing<16>* DecJob::rings<16>() { return r16; }
+template <> DecRing<8>*  DecJob::rings<8>()  { return r8; }
 
 template <int G, bool KNOWN>
 void dec_lane(int wl, DecJob* j)
@@ -25,8 +29,8 @@ void dec_lane(int wl, DecJob* j)
     const int grp = wl / G;
     const uint32_t gmask = (G == 32) ? 0xFFFFFFFFu : (((1u << G) - 1u) << leader);
     DecStream<G> st;
-    st.ring = &j->rings[grp]; st.lane = wl - leader; st.gmask = gmask;
-    for (int s = 0; s < DEC_SLOTS; s++) st.uses[s] = 0;
+    st.ring = &j->rings<G>()[grp]; st.lane = wl - leader; st.gmask = gmask;
+    st.gbase = 0;
     // every group walks the block list with a stride, like the kernel's dynamic hand-out
     for (int b = grp; b < j->nblocks; b += 32 / G) {
         int r = decode_block<G, KNOWN>(st, j->src[b], j->isize[b], j->dst[b], j->cap[b]);

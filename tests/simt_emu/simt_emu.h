@@ -48,7 +48,9 @@ static inline void stg_v4(void* p, uint4 v) { memcpy(p, &v, 16); }
 struct mbar_t { uint64_t v; };
 static inline void mbar_init(mbar_t* b, int) { b->v = 0; }
 // the copy "lands" at once and completes one barrier phase; waiters poll the phase parity like mbarrier.try_wait.parity
-static inline void bulk_g2s(void* sdst, const void* gsrc, uint32_t bytes, mbar_t* b) { memcpy(sdst, gsrc, bytes); b->v++; }
+// (the issuing lane runs expect + copies without yielding, so waiters never see a half-filled phase)
+static inline void mbar_expect(mbar_t* b, uint32_t) { b->v++; }
+static inline void bulk_copy(void* sdst, const void* gsrc, uint32_t bytes, mbar_t*) { memcpy(sdst, gsrc, bytes); }
 static inline void mbar_wait(mbar_t* b, uint32_t parity) { while ((b->v & 1) == (parity & 1)) simt_emu::yield(); }
 static inline void fence_mbar_init() {}
 }
