@@ -324,7 +324,9 @@ def main():
     peak_hbm = float(peaks.get("hbm_gbs", 6650.0)); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
 
     # ---- headline workload -------------------------------------------------------------------------------------------
-    work = Workload(ctx, args.blocks, args.cls, args.wave, seed=1, first_block=rank * args.blocks)
+    from lz4net_b200 import shard
+    first_block, _ = shard.weak_range(rank, args.blocks)        # rank r owns global blocks [r*B, (r+1)*B): no exchange step
+    work = Workload(ctx, args.blocks, args.cls, args.wave, seed=1, first_block=first_block)
     csum = work.verify()                                   # correctness first: full-batch round trip on the device
     raw_bytes = args.blocks * BLOCK
     nw = work.n_waves
@@ -352,13 +354,8 @@ def main():
     elapsed = t_start.elapsed_time(t_end) * 1e-3
     t_enc = sum(e[0][0].elapsed_time(e[0][1]) for e in evs) * 1e-3 / args.steps
     t_dec = sum(sum(p[0].elapsed_time(p[1]) for p in e[1:]) for e in evs) * 1e-3 / args.steps
-    if world > 1:
-        t = torch.tensor([elapsed, t_enc, t_dec], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed, t_enc, t_dec = (float(x) for x in t.tolist())
-        c = torch.tensor([csum], dtype=torch.float64, device="cuda"); dist.all_reduce(c); csum_all = float(c.item())
-    else:
-        csum_all = float(csum)
+    elapsed, t_enc, t_dec = shard.reduce_max([elapsed, t_enc, t_dec], device="cuda")     # the slowest rank defines the job
+    csum_all, = shard.reduce_sum([float(csum)], device="cuda")
     total_raw = raw_bytes * world
     value = total_raw * args.steps / elapsed / GB
     enc_gbs = total_raw / t_enc / GB; dec_gbs = total_raw / t_dec / GB
@@ -376,8 +373,7 @@ def main():
     if not args.no_e2e:
         r = e2e_host(ctx, args.cls, min(args.e2e_blocks, args.blocks), max(2, args.steps // 2), 1)
         te, td = r["t_enc"], r["t_dec"]
-        if world > 1:
-            t = torch.tensor([te, td], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); te, td = t.tolist()
+        te, td = shard.reduce_max([te, td], device="cuda")
         e2e = {"value": round(r["bytes"] * world / (te + td) / GB, 3), "unit": "GB/s", "h2d_bytes_per_step": int(r["h2d"]),
                "d2h_bytes_per_step": int(r["d2h"]), "encode_gbs": round(r["bytes"] * world / te / GB, 3),
                "decode_gbs": round(r["bytes"] * world / td / GB, 3),
