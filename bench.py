@@ -57,7 +57,7 @@ def parse():
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--sweep-blocks", type=int, default=1 << 16)
-    p.add_argument("--hc-blocks", type=int, default=1 << 14)
+    p.add_argument("--hc-blocks", type=int, default=1 << 16)
     return p.parse_args()
 
 
@@ -135,6 +135,21 @@ def cpu_codec(cls: str, n_blocks: int, threads: int, repeats: int = 3):
     return {"kind": kind, "encode_gbs": nbytes / best_e / GB, "decode_gbs": nbytes / best_d / GB,
             "roundtrip_gbs": nbytes / (best_e + best_d) / GB, "ratio": float(clen.sum()) / nbytes,
             "t_enc": best_e, "t_dec": best_d}
+
+
+def cpu_hc(cls: str, n_blocks: int, threads: int):
+    """LZ4HC encode of a small sample with the reference's C code on all host threads (GB/s raw)."""
+    import numpy as np
+    import oracle
+    from lz4net_b200 import synth
+    impl = "ref" if oracle.have_ref() else "port"
+    raw = synth.make_blocks(cls, n_blocks, BLOCK, seed=3).reshape(-1)
+    slot = oracle.bound(BLOCK)
+    so = np.arange(n_blocks, dtype=np.int64) * BLOCK; do = np.arange(n_blocks, dtype=np.int64) * slot
+    sl = np.full(n_blocks, BLOCK, np.int32); dc = np.full(n_blocks, slot, np.int32)
+    comp = np.zeros(n_blocks * slot + 64, np.uint8)
+    best = min(oracle.mt_run("encode_hc", impl, raw, so, sl, comp, do, dc, threads)[0] for _ in range(2))
+    return n_blocks * BLOCK / best / GB
 
 
 def run_reference(args):
@@ -410,7 +425,10 @@ def main():
             for wv in range(w.n_waves):
                 b0, b1 = w.decode_wave(wv); torch.cuda.synchronize()
                 assert torch.equal(w.out[: (b1 - b0) * BLOCK], w.raw[b0 * BLOCK: b1 * BLOCK]), "HC round trip failed"
-            hc[cls] = {"ratio": round(cs / rb, 4), "encode_gbs": round(rb / te / GB, 2), "blocks": w.n}
+            hc[cls] = {"ratio": round(cs / rb, 4), "encode_gbs": round(rb / te / GB, 2), "blocks": w.n,
+                       "roofline_frac": round((rb + cs) / te / GB / peak_hbm, 5)}
+            if not args.no_cpu:
+                hc[cls]["cpu_reference_gbs"] = round(cpu_hc(cls, 1024 if cls == "ETEXT" else 4096, os.cpu_count() or 1), 3)
             del w; torch.cuda.empty_cache()
         extras["hc"] = hc
     cpu = None

@@ -4,6 +4,8 @@ Only the hot path lives here: hand-written CUDA kernels (csrc/), their C ABI (in
 the host-side mirror of the reference interface (codec.py).  There is no CPU codec in this package.
 """
 from . import native, synth  # noqa: F401
-from .codec import Context, CudaLZ4Service, LZ4Codec, default_context  # noqa: F401
+from .codec import (Context, CudaLZ4Service, LZ4Codec, LZ4Stream, LZ4StreamFlags, LZ4StreamMode,  # noqa: F401
+                    default_context)
 
-__all__ = ["native", "synth", "Context", "CudaLZ4Service", "LZ4Codec", "default_context"]
+__all__ = ["native", "synth", "Context", "CudaLZ4Service", "LZ4Codec", "LZ4Stream", "LZ4StreamFlags", "LZ4StreamMode",
+           "default_context"]

@@ -288,3 +288,137 @@ class LZ4Codec:
         if r < 0:
             raise ValueError("LZ4 block is corrupted, or invalid length has been given.")
         return dst[:r].tobytes()
+
+
+class LZ4StreamMode:
+    Compress, Decompress = 0, 1                                       # src/LZ4/LZ4StreamMode.cs
+
+
+class LZ4StreamFlags:
+    None_, InteractiveRead, HighCompression, IsolateInnerStream, Default = 0, 1, 2, 4, 0    # src/LZ4/LZ4StreamFlags.cs
+
+
+class LZ4Stream:
+    """``LZ4Stream`` (src/LZ4/LZ4Stream.cs) over a Python binary file object.
+
+    Wire format and chunk boundaries are the reference's (a chunk per ``blockSize`` bytes written, a partial chunk on
+    ``Flush``/``Close``, FlushCurrentChunk :239-269); the dispatcher differs: up to ``batchBlocks`` buffered blocks are
+    encoded / decoded by ONE batched GPU call instead of one block per call."""
+
+    def __init__(self, innerStream, compressionMode, compressionFlags=LZ4StreamFlags.Default, blockSize=1024 * 1024,
+                 batchBlocks=256, context: Optional[Context] = None):
+        self._inner = innerStream
+        self._mode = compressionMode
+        self._hc = bool(compressionFlags & LZ4StreamFlags.HighCompression)
+        self._interactive = bool(compressionFlags & LZ4StreamFlags.InteractiveRead)
+        self._isolate = bool(compressionFlags & LZ4StreamFlags.IsolateInnerStream)
+        self._block = max(16, int(blockSize))                          # :131,138
+        self._batch = max(1, int(batchBlocks))
+        self._ctx = context or default_context()
+        self._pending = bytearray()
+        self._ready = b""
+        self._rpos = 0
+        self._closed = False
+
+    CanSeek = False
+
+    @property
+    def CanRead(self):
+        return self._mode == LZ4StreamMode.Decompress
+
+    @property
+    def CanWrite(self):
+        return self._mode == LZ4StreamMode.Compress
+
+    # ---- write side (:444-470) ----
+    def Write(self, buffer, offset=0, count=None):
+        if not self.CanWrite:
+            raise NotImplementedError("Operation 'Write' is not supported")
+        count = len(buffer) - offset if count is None else count
+        self._pending += bytes(buffer[offset:offset + count])
+        full = self._batch * self._block
+        while len(self._pending) > full:          # a full buffer is flushed only when more data arrives (:463-467)
+            self._emit(full)
+
+    def WriteByte(self, value):
+        self.Write(bytes([value]))
+
+    def _emit(self, n):
+        self._inner.write(self._ctx.stream_encode(bytes(self._pending[:n]), self._block, self._hc))
+        del self._pending[:n]
+
+    def Flush(self):                                                    # :337-340
+        if self.CanWrite and self._pending:
+            self._emit(len(self._pending))
+
+    def Close(self):                                                    # Dispose :472-478
+        if not self._closed:
+            self.Flush()
+            self._closed = True
+            if not self._isolate and hasattr(self._inner, "close"):
+                self._inner.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.Close()
+
+    # ---- read side (:376-401, AcquireNextChunk :274-312) ----
+    def _read_varint(self, raw, first):
+        v, count = 0, 0
+        while True:
+            b = self._inner.read(1)
+            if not b:
+                if first and count == 0:
+                    return None
+                raise EOFError("Unexpected end of stream")
+            raw += b
+            v += (b[0] & 0x7F) << count
+            count += 7
+            if not (b[0] & 0x80) or count >= 64:
+                return v
+
+    def _acquire(self):
+        raw = bytearray()
+        for _ in range(self._batch):
+            flags = self._read_varint(raw, True)
+            if flags is None:
+                break
+            raw_len = self._read_varint(raw, False)
+            comp_len = self._read_varint(raw, False) if flags & 1 else raw_len
+            if comp_len > raw_len:
+                raise EOFError("Unexpected end of stream")             # :288 corrupted
+            payload = self._inner.read(comp_len)
+            while len(payload) < comp_len:                              # ReadBlock :205-221: no partial chunks
+                more = self._inner.read(comp_len - len(payload))
+                if not more:
+                    raise EOFError("Unexpected end of stream")
+                payload += more
+            raw += payload
+        if not raw:
+            return False
+        self._ready = self._ctx.stream_decode(bytes(raw))
+        self._rpos = 0
+        return True
+
+    def Read(self, count):
+        """Returns up to `count` bytes (b"" at end of stream); with InteractiveRead returns as soon as it has any."""
+        if not self.CanRead:
+            raise NotImplementedError("Operation 'Read' is not supported")
+        out = bytearray()
+        while count > 0:
+            chunk = min(count, len(self._ready) - self._rpos)
+            if chunk > 0:
+                out += self._ready[self._rpos:self._rpos + chunk]
+                self._rpos += chunk
+                if self._interactive:
+                    break
+                count -= chunk
+            elif not self._acquire():
+                break
+        return bytes(out)
+
+    def ReadByte(self):
+        b = self.Read(1)
+        return b[0] if b else -1

@@ -323,3 +323,42 @@ def test_compact_scan(ctx):
         for i in list(range(0, n, max(1, n // 50))):
             l = max(int(lens[i]), 0)
             assert np.array_equal(hp[want[i]:want[i] + l], hs[i, :l])
+
+
+@pytest.mark.parametrize("hc", [False, True])
+def test_lz4stream_class_random_writes_and_reads(ctx, hc):
+    """src/LZ4.Tests/StreamTests.cs:47-63,148-181: random-length writes (with occasional Flush), then read everything
+    back in random-length reads, normal and InteractiveRead; the wire bytes equal the reference format chunk by chunk."""
+    import io
+    from lz4net_b200 import LZ4Stream, LZ4StreamFlags, LZ4StreamMode
+    rng = np.random.default_rng(17)
+    data = b"".join(cases.content(m, n, seed=4).tobytes() for m, n in (("ETEXT", 300000), ("E0", 100000), ("mixed", 60000), ("E100", 250000)))
+    for bs in (65536, 4096):
+        inner = io.BytesIO()
+        flags = LZ4StreamFlags.IsolateInnerStream | (LZ4StreamFlags.HighCompression if hc else 0)
+        cuts = [0]
+        with LZ4Stream(inner, LZ4StreamMode.Compress, flags, bs, batchBlocks=7, context=ctx) as s:
+            pos = 0
+            while pos < len(data):
+                k = int(min(len(data) - pos, rng.integers(1, 90000)))
+                s.Write(data, pos, k); pos += k
+                if rng.integers(0, 6) == 0:
+                    s.Flush(); cuts.append(pos)
+        cuts.append(len(data))
+        wire = inner.getvalue()
+        # a Flush ends the current chunk: the stream is the concatenation of independently framed segments
+        assert wire == b"".join(_ref_stream(data[a:b], bs, hc) for a, b in zip(cuts, cuts[1:]))
+        for interactive in (False, True):
+            r = LZ4Stream(io.BytesIO(wire), LZ4StreamMode.Decompress,
+                          LZ4StreamFlags.InteractiveRead if interactive else LZ4StreamFlags.Default, batchBlocks=5, context=ctx)
+            back = bytearray()
+            while True:
+                want = int(rng.integers(1, 200000))
+                got = r.Read(want)
+                if not got:
+                    break
+                assert interactive or len(got) == want or len(back) + len(got) == len(data)
+                back += got
+            assert bytes(back) == data
+        with pytest.raises(EOFError):
+            LZ4Stream(io.BytesIO(wire[:-2]), LZ4StreamMode.Decompress, context=ctx).Read(len(data) + 1)
