@@ -118,7 +118,7 @@ int lz4b200_synth_fill(lz4b200_ctx* ctx, void* dst, int64_t n_blocks, int32_t bl
                        int64_t first_block, void* stream);
 
 /* Tuning knobs (bench / profiling only).  key: "decode_lanes" (8|16|32 lanes per block), "encode_ctas_per_sm",
- * "hc_concurrency" (blocks in flight).  Returns LZ4B200_OK or LZ4B200_E_ARG. */
+ * "hc_concurrency" (blocks in flight), "host_chunk_mb" (bytes per pipeline stage of host-memory batches).  Returns LZ4B200_OK or LZ4B200_E_ARG. */
 int lz4b200_set_option(lz4b200_ctx* ctx, const char* key, int64_t value);
 
 /* Kernel launches issued through this context since creation (bench.py reports it as gpu_launches). */

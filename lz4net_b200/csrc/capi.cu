@@ -32,7 +32,7 @@ int cuda_fail(cudaError_t e, const char* what)
 
 constexpr int NSLOT = 3;                       // pipeline depth of host-memory batches
 constexpr int NCOUNTER = 256;
-constexpr size_t HOST_CHUNK_BYTES = 96u << 20; // raw bytes per pipeline stage
+constexpr size_t HOST_CHUNK_BYTES_DEFAULT = 96u << 20; // src + dst bytes per pipeline stage
 
 struct DevBuf {
     void* p = nullptr; size_t cap = 0;
@@ -80,6 +80,7 @@ struct lz4b200_ctx {
     DevBuf hc_arena, compact_tmp;
     int decode_lanes = 16;
     int encode_ctas_per_sm = 0;            // 0 = as many as shared memory allows
+    size_t host_chunk_bytes = HOST_CHUNK_BYTES_DEFAULT;
     int hc_concurrency = 65536;          // blocks in flight (one thread each, 256 KiB state): measured 3x over 16384
     Slot slot[NSLOT];
     int64_t launches = 0;
@@ -156,7 +157,7 @@ int run_host(lz4b200_ctx* c, const uint8_t* src, const int64_t* src_off, const i
         int64_t bytes = 0; int32_t b1 = b0;
         while (b1 < n) {
             int64_t w = std::max<int64_t>(src_len[b1], 0) + std::max<int64_t>(dst_cap[b1], 0);
-            if (b1 > b0 && bytes + w > (int64_t)HOST_CHUNK_BYTES) break;
+            if (b1 > b0 && bytes + w > (int64_t)c->host_chunk_bytes) break;
             bytes += w; b1++;
         }
         const int s = k % NSLOT; k++;
@@ -381,6 +382,7 @@ int lz4b200_set_option(lz4b200_ctx* c, const char* key, int64_t value)
         c->hc_arena.release();
         c->hc_concurrency = (int)value;
     }
+    else if (k == "host_chunk_mb") { if (value < 1 || value > 4096) return fail(LZ4B200_E_ARG, "host_chunk_mb out of range"); c->host_chunk_bytes = (size_t)value << 20; }
     else return fail(LZ4B200_E_ARG, "unknown option");
     return LZ4B200_OK;
 }

@@ -40,6 +40,20 @@ SIMT_DEV uint32_t in32(const uint8_t* src, int p)
     return simt::funnel_r(lo, hi, sh);
 }
 
+// The same read through a per-block word view of the input: base rounded down to 4 bytes + a 32-bit word index, so the
+// address is one IMAD.WIDE instead of a 64-bit add, align and re-add.
+struct InWords {
+    const uint32_t* w; uint32_t sk;
+    SIMT_MEM void init(const uint8_t* src) { sk = (uint32_t)((uintptr_t)src & 3); w = (const uint32_t*)(src - sk); }
+    SIMT_MEM uint32_t at(int p) const
+    {
+        const uint32_t q = (uint32_t)p + sk, i = q >> 2, sh = (q & 3u) * 8u;
+        const uint32_t lo = simt::ldg_nc_u32(w + i);
+        const uint32_t hi = sh ? simt::ldg_nc_u32(w + i + 1) : 0u;
+        return simt::funnel_r(lo, hi, sh);
+    }
+};
+
 // ---- source policies -------------------------------------------------------------------------------------------
 // Ring in shared memory: byte i of the source lives at buf[(pos0 + i) & (SIZE-1)].
 template <int SIZE>

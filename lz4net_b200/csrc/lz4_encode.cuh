@@ -29,6 +29,10 @@ constexpr int LZ4_64KLIMIT = 65547;                                // original/l
 // token length extension: `v` as a run of 255s plus a remainder byte, written lane-parallel; returns bytes written
 SIMT_DEV int put_len_ext(uint8_t* dst, int op, int cap, int v, int lane)
 {
+    if (v < 255) {                                                 // the common case: one byte
+        if (lane == 0 && op < cap) simt::stg_u8(dst + op, (uint8_t)v);
+        return 1;
+    }
     const int nff = v / 255;
     for (int i = lane; i < nff; i += 32) if (op + i < cap) simt::stg_u8(dst + op + i, 255);
     if (lane == 0 && op + nff < cap) simt::stg_u8(dst + op + nff, (uint8_t)(v - nff * 255));
@@ -45,6 +49,7 @@ SIMT_DEV int encode_block_t(EncShared* sh, const uint8_t* src, int n, uint8_t* d
     const int mflimit = n - 12, matchlimit = n - 5;                // :361,:366 / :590,:596
     int ip = 0, anchor = 0, op = 0, ref = 0, tok = 0;
     uint32_t tokval = 0;
+    InWords in; in.init(src);
 
     for (int i = lane; i < 1024; i += 32) ((uint4*)sh->table)[i] = uint4{0, 0, 0, 0};
     simt::syncwarp(FULL);
@@ -57,13 +62,17 @@ SIMT_DEV int encode_block_t(EncShared* sh, const uint8_t* src, int n, uint8_t* d
             int p0 = ip;
             bool finished = false;
             for (;;) {
-                const int q = (int)(A >> 6), cross = 64 - (int)(A & 63);
-                const int bump = lane - cross;                     // attempts before `lane` that already use step q+1
-                const int pos = p0 + q * lane + (bump > 0 ? bump : 0);
-                const int nxt = pos + q + (lane >= cross ? 1 : 0);
+                int pos, nxt;
+                if (A == (1u << 6) + 3) { pos = p0 + lane; nxt = pos + 1; }      // first round: 32 attempts, all with step 1
+                else {
+                    const int q = (int)(A >> 6), cross = 64 - (int)(A & 63);
+                    const int bump = lane - cross;                 // attempts before `lane` that already use step q+1
+                    pos = p0 + q * lane + (bump > 0 ? bump : 0);
+                    nxt = pos + q + (lane >= cross ? 1 : 0);
+                }
                 const bool valid = nxt <= mflimit;                 // the bounds test precedes the probe (:420 / :648)
                 uint32_t v = 0, h = 0x80000000u | (uint32_t)lane;  // invalid lanes get a key nobody shares
-                if (valid) { v = in32(src, pos); h = (v * 2654435761u) >> HSHIFT; }
+                if (valid) { v = in.at(pos); h = (v * 2654435761u) >> HSHIFT; }
                 const uint32_t same = simt::match_any(FULL, h);
                 const uint32_t lower = same & ((1u << lane) - 1u);
                 const int from = lower ? 31 - simt::clz(lower) : lane;
@@ -71,7 +80,7 @@ SIMT_DEV int encode_block_t(EncShared* sh, const uint8_t* src, int n, uint8_t* d
                 int cand = 0; bool hit = false;
                 if (valid) {
                     cand = lower ? fwd : (GENERAL ? (int)T32[h] : (int)T16[h]);
-                    hit = (!GENERAL || cand >= pos - 65535) && in32(src, cand) == v;        // :429 / :654
+                    hit = (!GENERAL || cand >= pos - 65535) && in.at(cand) == v;        // :429 / :654
                 }
                 const uint32_t stop = simt::ballot(FULL, !valid || hit);
                 const int f = stop ? simt::ffs(stop) - 1 : 32;
@@ -128,7 +137,7 @@ SIMT_DEV int encode_block_t(EncShared* sh, const uint8_t* src, int n, uint8_t* d
                     int room = matchlimit - a; room = room < 0 ? 0 : (room > 4 ? 4 : room);
                     int cnt = 0;
                     if (room > 0) {
-                        const uint32_t x = in32(src, a) ^ in32(src, ref + 4 * lane);
+                        const uint32_t x = in.at(a) ^ in.at(ref + 4 * lane);
                         cnt = x ? (simt::ffs(x) - 1) >> 3 : 4;
                         if (cnt > room) cnt = room;
                     }
@@ -150,8 +159,8 @@ SIMT_DEV int encode_block_t(EncShared* sh, const uint8_t* src, int n, uint8_t* d
                 if (ip > mflimit) { anchor = ip; finished = true; break; }      // :516 / :736
                 // table fix-up for ip-2, then probe ip itself (:519-531 / :739-751); reads first, then lane 0 writes
                 const int p2 = ip - 2;
-                const uint32_t h2 = (in32(src, p2) * 2654435761u) >> HSHIFT;
-                const uint32_t vi = in32(src, ip);
+                const uint32_t h2 = (in.at(p2) * 2654435761u) >> HSHIFT;
+                const uint32_t vi = in.at(ip);
                 const uint32_t h = (vi * 2654435761u) >> HSHIFT;
                 ref = (h == h2) ? p2 : (GENERAL ? (int)T32[h] : (int)T16[h]);
                 simt::syncwarp(FULL);
@@ -160,7 +169,7 @@ SIMT_DEV int encode_block_t(EncShared* sh, const uint8_t* src, int n, uint8_t* d
                     else         { T16[h2] = (uint16_t)p2; T16[h] = (uint16_t)ip; }
                 }
                 simt::syncwarp(FULL);
-                if ((!GENERAL || ref > ip - 65536) && in32(src, ref) == vi) {
+                if ((!GENERAL || ref > ip - 65536) && in.at(ref) == vi) {
                     tok = op++; tokval = 0; again = true;          // zero-literal sequence (:531 / :751)
                 }
             } while (again);
