@@ -56,7 +56,7 @@ def parse():
     p.add_argument("--no-hc", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
-    p.add_argument("--sweep-blocks", type=int, default=1 << 16)
+    p.add_argument("--sweep-blocks", type=int, default=1 << 17)
     p.add_argument("--hc-blocks", type=int, default=1 << 16)
     return p.parse_args()
 
@@ -279,18 +279,20 @@ def e2e_host(ctx, cls, n_blocks, steps, warmup):
     for b0 in range(0, n_blocks, gen):
         m = min(gen, n_blocks - b0)
         raw[b0 * BLOCK:(b0 + m) * BLOCK] = torch.from_numpy(synth.make_blocks(cls, m, BLOCK, seed=7, first_block=b0).reshape(-1))
-    comp = torch.empty(n_blocks * slot, dtype=torch.uint8).pin_memory()
+    comp = torch.empty(n_blocks * slot, dtype=torch.uint8).pin_memory()       # packed payloads land here back to back
     out = torch.empty(n_blocks * BLOCK, dtype=torch.uint8).pin_memory()
-    so = np.arange(n_blocks, dtype=np.int64) * BLOCK; do = np.arange(n_blocks, dtype=np.int64) * slot
+    so = np.arange(n_blocks, dtype=np.int64) * BLOCK
     sl = np.full(n_blocks, BLOCK, np.int32); dc = np.full(n_blocks, slot, np.int32)
-    clen = np.zeros(n_blocks, np.int32); used = np.zeros(n_blocks, np.int32)
+    clen = np.zeros(n_blocks, np.int32); used = np.zeros(n_blocks, np.int32); coff = np.zeros(n_blocks + 1, np.int64)
 
     def once():
         t0 = time.perf_counter()
-        ctx.encode_batch_ptr(raw.data_ptr(), so.ctypes.data, sl.ctypes.data, comp.data_ptr(), do.ctypes.data, dc.ctypes.data,
-                             clen.ctypes.data, n_blocks, hc=False, device=False)
+        # encode: raw blocks in host memory -> packed compressed payloads + offsets in host memory
+        ctx.encode_batch_packed_ptr(raw.data_ptr(), so.ctypes.data, sl.ctypes.data, dc.ctypes.data, comp.data_ptr(), comp.numel(),
+                                    coff.ctypes.data, clen.ctypes.data, n_blocks, hc=False)
         t1 = time.perf_counter()
-        ctx.decode_batch_ptr(comp.data_ptr(), do.ctypes.data, clen.ctypes.data, out.data_ptr(), so.ctypes.data, sl.ctypes.data,
+        # decode: the packed payloads -> raw blocks in host memory
+        ctx.decode_batch_ptr(comp.data_ptr(), coff.ctypes.data, clen.ctypes.data, out.data_ptr(), so.ctypes.data, sl.ctypes.data,
                              used.ctypes.data, n_blocks, known=True, device=False)
         t2 = time.perf_counter()
         return t1 - t0, t2 - t1
@@ -303,9 +305,9 @@ def e2e_host(ctx, cls, n_blocks, steps, warmup):
     te /= steps; td /= steps
     nbytes = n_blocks * BLOCK
     csum = int(clen.sum())
-    # per step: encode copies raw in / whole slots out; decode copies the slot range in / raw out
-    h2d = nbytes + n_blocks * slot
-    d2h = n_blocks * slot + nbytes
+    # per step: encode copies raw in / packed payload out; decode copies the packed payload in / raw out
+    h2d = nbytes + csum
+    d2h = csum + nbytes
     return {"t_enc": te, "t_dec": td, "bytes": nbytes, "h2d": h2d, "d2h": d2h, "compressed": csum}
 
 
@@ -327,8 +329,11 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import lz4net_b200
     ctx = lz4net_b200.Context(local)
-    if args.lanes:
-        ctx.set_option("decode_lanes", args.lanes)
+    # decode group size per entropy class (tools/sweep.py, profiles/sweep_r01.txt): lanes per block, +100 = the
+    # shared-memory output-staged variant.  Long-run data wants whole warps, sequence-dense data sub-warp groups.
+    TUNED_LANES = {"E0": 32, "E50": 108, "E100": 16, "ETEXT": 8}
+    lanes_for = lambda cls: args.lanes or TUNED_LANES[cls]
+    ctx.set_option("decode_lanes", lanes_for(args.cls))
     if args.enc_ctas:
         ctx.set_option("encode_ctas_per_sm", args.enc_ctas)
     peaks = {}
@@ -392,7 +397,7 @@ def main():
         e2e = {"value": round(r["bytes"] * world / (te + td) / GB, 3), "unit": "GB/s", "h2d_bytes_per_step": int(r["h2d"]),
                "d2h_bytes_per_step": int(r["d2h"]), "encode_gbs": round(r["bytes"] * world / te / GB, 3),
                "decode_gbs": round(r["bytes"] * world / td / GB, 3),
-               "sample": f"{min(args.e2e_blocks, args.blocks)} x 64 KiB blocks per GPU in pinned host memory through lz4b200_encode_batch + lz4b200_decode_batch (MEM_HOST), wall clock"}
+               "sample": f"{min(args.e2e_blocks, args.blocks)} x 64 KiB blocks per GPU in pinned host memory through lz4b200_encode_batch_packed + lz4b200_decode_batch (MEM_HOST), wall clock"}
 
     if rank != 0:
         if world > 1:
@@ -406,13 +411,15 @@ def main():
     if world == 1 and not args.no_sweep:
         sweep = {}
         for cls in ("E0", "E50", "E100", "ETEXT"):
+            ctx.set_option("decode_lanes", lanes_for(cls))
             w = Workload(ctx, min(args.sweep_blocks, args.blocks), cls, args.wave, seed=2)
             cs = w.verify()
             te, td = measure_pair(w, 3, 2)
             rb = w.n * BLOCK
             sweep[cls] = {"ratio": round(cs / rb, 4), "encode_gbs": round(rb / te / GB, 1), "decode_gbs": round(rb / td / GB, 1),
                           "decode_roofline_frac": round((rb + cs) / td / GB / peak_hbm, 4),
-                          "encode_roofline_frac": round((rb + cs) / te / GB / peak_hbm, 4), "blocks": w.n}
+                          "encode_roofline_frac": round((rb + cs) / te / GB / peak_hbm, 4), "blocks": w.n,
+                          "decode_lanes": lanes_for(cls)}
             del w; torch.cuda.empty_cache()
         extras["entropy_sweep"] = sweep
     if world == 1 and not args.no_hc:
@@ -448,6 +455,7 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": f"{args.blocks} x 64KiB independent blocks per GPU, class {args.cls} (BASELINE configs[1]): one fast-encode launch + {nw} known-size decode launches per step",
                    "block_size": BLOCK, "class": args.cls, "blocks_per_gpu": args.blocks, "ratio": round(csum_all / total_raw, 4),
+                   "decode_lanes": lanes_for(args.cls),
                    "decode_wave_blocks": work_wave(args), "l2": "inputs (64 GiB raw + slots per GPU) are far larger than the 126 MB L2; no flush needed",
                    "parallelism": f"independent blocks sharded over {world} GPU(s), no data-path collective", "gb": "1e9 bytes"},
         "encode_gbs": round(enc_gbs, 2), "decode_gbs": round(dec_gbs, 2),

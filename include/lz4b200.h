@@ -78,6 +78,16 @@ int lz4b200_decode_batch(lz4b200_ctx* ctx,
                          void* dst, const int64_t* dst_off, const int32_t* dst_cap,
                          int32_t* out_len, int32_t n_blocks, int known_len, int mem, void* stream);
 
+/* Host-memory encode with PACKED output: block i's compressed bytes land at dst + out_off[i] (out_off has n_blocks+1
+ * entries; out_off[n_blocks] = total bytes written <= dst_total_cap), back to back in block order -- the layout the
+ * LZ4Stream chunk writer (src/LZ4/LZ4Stream.cs:262-266) and any transport want, and the one that moves only compLen
+ * bytes per block back over PCIe.  dst_cap[i] is still the per-block limit of LZ4_compress_limitedOutput (a block that
+ * does not fit reports out_len[i] = 0 and occupies no bytes). */
+int lz4b200_encode_batch_packed(lz4b200_ctx* ctx,
+                                const void* src, const int64_t* src_off, const int32_t* src_len, const int32_t* dst_cap,
+                                void* dst, int64_t dst_total_cap, int64_t* out_off, int32_t* out_len,
+                                int32_t n_blocks, int mode);
+
 /* Compaction of fixed-stride encoder slots into one contiguous payload (device memory only): the batched form of
  * the Buffer.BlockCopy trim in LZ4Codec.Encode (src/LZ4/LZ4Codec.cs:357-364).  out_off[i] (int64, n_blocks+1
  * entries) = exclusive prefix sum of max(len[i],0); block i's bytes are copied to packed + out_off[i]. */

@@ -67,6 +67,26 @@ class Context:
                                                        1 if known else 0,
                                                        native.MEM_DEVICE if device else native.MEM_HOST, stream), "decode_batch")
 
+    def encode_batch_packed_ptr(self, src, src_off, src_len, dst_cap, dst, dst_total_cap, out_off, out_len, n, hc=False):
+        native.check(native.lib().lz4b200_encode_batch_packed(self._h, src, src_off, src_len, dst_cap, dst, int(dst_total_cap),
+                                                              out_off, out_len, int(n),
+                                                              native.MODE_HC if hc else native.MODE_FAST), "encode_batch_packed")
+
+    def encode_blocks_packed(self, blocks, caps=None, hc=False):
+        """Host batch with packed output.  Returns (out_len list, out_off list[n+1], packed bytes)."""
+        n = len(blocks)
+        lens = np.array([len(b) for b in blocks], np.int32)
+        caps = np.array([native.lib().lz4b200_compress_bound(int(l)) for l in lens] if caps is None else caps, np.int32)
+        src_off = np.concatenate([[0], np.cumsum(lens, dtype=np.int64)[:-1]]).astype(np.int64) if n else np.zeros(0, np.int64)
+        src = np.frombuffer(b"".join(bytes(b) for b in blocks) + b"\0" * 16, np.uint8)
+        total_cap = int(caps.sum())
+        dst = np.full(total_cap + 16, 0xEE, np.uint8)
+        out = np.zeros(n, np.int32); off = np.zeros(n + 1, np.int64)
+        self.encode_batch_packed_ptr(src.ctypes.data, src_off.ctypes.data, lens.ctypes.data, caps.ctypes.data, dst.ctypes.data,
+                                     total_cap, off.ctypes.data, out.ctypes.data, n, hc=hc)
+        assert (dst[int(off[n]):] == 0xEE).all(), "packed encode wrote past the reported total"
+        return out.tolist(), off.tolist(), dst[:int(off[n])].tobytes()
+
     # ---- numpy (host memory) convenience -----------------------------------------------------------------------
     def encode_blocks(self, blocks, caps=None, hc=False):
         """blocks: list of bytes-like.  Returns (out_len list, list of bytes) -- one host-memory batch call."""

@@ -32,7 +32,7 @@ int cuda_fail(cudaError_t e, const char* what)
 
 constexpr int NSLOT = 3;                       // pipeline depth of host-memory batches
 constexpr int NCOUNTER = 256;
-constexpr size_t HOST_CHUNK_BYTES_DEFAULT = 96u << 20; // src + dst bytes per pipeline stage
+constexpr size_t HOST_CHUNK_BYTES_DEFAULT = 256u << 20; // src + dst bytes per pipeline stage
 
 struct DevBuf {
     void* p = nullptr; size_t cap = 0;
@@ -65,7 +65,7 @@ struct PinBuf {
 struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
-    DevBuf src, dst, meta;
+    DevBuf src, dst, meta, packed, offs, scan;
     PinBuf hmeta;
 };
 
@@ -78,6 +78,7 @@ struct lz4b200_ctx {
     uint32_t* counters = nullptr;
     int next_counter = 0;
     DevBuf hc_arena, compact_tmp;
+    cudaEvent_t hc_done = nullptr;         // the HC state arena is shared: HC launches are chained through this event
     int decode_lanes = 16;
     int encode_ctas_per_sm = 0;            // 0 = as many as shared memory allows
     size_t host_chunk_bytes = HOST_CHUNK_BYTES_DEFAULT;
@@ -109,7 +110,10 @@ int run_device(lz4b200_ctx* c, const BatchArgs& a, int op /*0 enc fast, 1 enc hc
             CU(cudaDeviceSynchronize());           // the arena may still be in use by an earlier launch
             CU(c->hc_arena.reserve(need));
         }
+        // one arena per context: an HC launch may not overlap the previous one, whatever stream it was given
+        CU(cudaStreamWaitEvent(st, c->hc_done, 0));
         e = launch_encode_hc(a, c->hc_arena.p, conc, c->counter(), c->dev, st, &c->launches);
+        if (e == cudaSuccess) e = cudaEventRecord(c->hc_done, st);
         break;
     }
     case 2: e = launch_decode(a, true, c->decode_lanes, c->counter(), c->dev, st, &c->launches); break;
@@ -210,6 +214,84 @@ int run_host(lz4b200_ctx* c, const uint8_t* src, const int64_t* src_off, const i
     return LZ4B200_OK;
 }
 
+// Host-memory encode with PACKED output: per chunk  H2D(raw) -> encode into device slots -> compact on the device ->
+// D2H(exactly the compressed bytes).  Only compLen bytes per block cross PCIe on the way back (LZ4Stream / RPC payloads
+// want the packed form anyway).  out_off[n+1] receives the byte offset of every block's payload in dst.
+int run_host_encode_packed(lz4b200_ctx* c, const uint8_t* src, const int64_t* src_off, const int32_t* src_len,
+                           const int32_t* dst_cap, uint8_t* dst, int64_t dst_total_cap, int64_t* out_off, int32_t* out_len,
+                           int32_t n, int op)
+{
+    int32_t b0 = 0; int k = 0; int64_t written = 0;
+    struct Pending { int32_t b0, b1; int32_t* h_out; int64_t* h_off; };
+    Pending pend[NSLOT]; bool busy[NSLOT] = {false, false, false};
+
+    auto retire = [&](int s) -> int {
+        if (!busy[s]) return LZ4B200_OK;
+        Slot& sl = c->slot[s]; Pending& p = pend[s];
+        CU(cudaStreamSynchronize(sl.stream));                        // lengths and local offsets are on the host now
+        const int32_t m = p.b1 - p.b0;
+        const int64_t total = p.h_off[m];
+        if (written + total > dst_total_cap) return fail(LZ4B200_E_ARG, "packed destination too small");
+        if (total > 0) CU(cudaMemcpyAsync(dst + written, sl.packed.p, (size_t)total, cudaMemcpyDeviceToHost, sl.stream));
+        std::memcpy(out_len + p.b0, p.h_out, sizeof(int32_t) * (size_t)m);
+        for (int32_t i = 0; i < m; i++) out_off[p.b0 + i] = written + p.h_off[i];
+        written += total;
+        CU(cudaStreamSynchronize(sl.stream));
+        busy[s] = false;
+        return LZ4B200_OK;
+    };
+
+    while (b0 < n) {
+        int64_t bytes = 0; int32_t b1 = b0;
+        while (b1 < n) {
+            if (src_len[b1] < 0 || dst_cap[b1] < 0) return fail(LZ4B200_E_ARG, "negative block length");
+            int64_t w = (int64_t)src_len[b1] + dst_cap[b1];
+            if (b1 > b0 && bytes + w > (int64_t)c->host_chunk_bytes) break;
+            bytes += w; b1++;
+        }
+        const int s = k % NSLOT; k++;
+        // payloads must land in block order: retire every older chunk first (its D2H overlaps this chunk's H2D + kernel
+        // only through the other slots' streams)
+        int rc = retire(s); if (rc) return rc;
+        Slot& sl = c->slot[s];
+        const int32_t m = b1 - b0;
+        int64_t slo = INT64_MAX, shi = INT64_MIN, dsum = 0;
+        for (int32_t i = b0; i < b1; i++) { slo = std::min(slo, src_off[i]); shi = std::max(shi, src_off[i] + src_len[i]); dsum += dst_cap[i]; }
+        const size_t sbytes = (size_t)(shi - slo);
+        CU(sl.src.reserve(sbytes + 64)); CU(sl.dst.reserve((size_t)dsum + 64)); CU(sl.packed.reserve((size_t)dsum + 64));
+        CU(sl.offs.reserve(sizeof(int64_t) * (size_t)(m + 1))); CU(sl.scan.reserve(compact_tmp_bytes(m)));
+        const size_t meta_bytes = (size_t)m * 28 + sizeof(int64_t) * (size_t)(m + 1);
+        CU(sl.meta.reserve((size_t)m * 28)); CU(sl.hmeta.reserve(meta_bytes + 64));
+        int64_t* h_so = (int64_t*)sl.hmeta.p; int64_t* h_do = h_so + m;
+        int32_t* h_sl = (int32_t*)(h_do + m); int32_t* h_dc = h_sl + m; int32_t* h_out = h_dc + m;
+        int64_t* h_off = (int64_t*)(((uintptr_t)(h_out + m) + 7) & ~(uintptr_t)7);
+        int64_t acc = 0;
+        for (int32_t i = 0; i < m; i++) {
+            h_so[i] = src_off[b0 + i] - slo; h_do[i] = acc; acc += dst_cap[b0 + i];
+            h_sl[i] = src_len[b0 + i]; h_dc[i] = dst_cap[b0 + i];
+        }
+        uint8_t* d_meta = (uint8_t*)sl.meta.p;
+        CU(cudaMemcpyAsync(d_meta, sl.hmeta.p, (size_t)m * 24, cudaMemcpyHostToDevice, sl.stream));
+        if (sbytes) CU(cudaMemcpyAsync(sl.src.p, src + slo, sbytes, cudaMemcpyHostToDevice, sl.stream));
+        BatchArgs a;
+        a.src = (const uint8_t*)sl.src.p; a.dst = (uint8_t*)sl.dst.p;
+        a.src_off = (const int64_t*)d_meta; a.dst_off = a.src_off + m;
+        a.src_len = (const int32_t*)(a.dst_off + m); a.dst_cap = a.src_len + m;
+        a.out_len = (int32_t*)(a.dst_cap + m); a.n_blocks = m;
+        rc = run_device(c, a, op, sl.stream); if (rc) return rc;
+        cudaError_t e = launch_compact(a.dst, a.dst_off, a.out_len, (uint8_t*)sl.packed.p, (int64_t*)sl.offs.p, m,
+                                       sl.scan.p, sl.scan.cap, c->dev, sl.stream, &c->launches);
+        if (e != cudaSuccess) return cuda_fail(e, "compact launch");
+        CU(cudaMemcpyAsync(h_out, a.out_len, sizeof(int32_t) * (size_t)m, cudaMemcpyDeviceToHost, sl.stream));
+        CU(cudaMemcpyAsync(h_off, sl.offs.p, sizeof(int64_t) * (size_t)(m + 1), cudaMemcpyDeviceToHost, sl.stream));
+        pend[s] = Pending{b0, b1, h_out, h_off}; busy[s] = true;
+        b0 = b1;
+    }
+    for (int i = 0; i < NSLOT; i++) { int rc = retire((k + i) % NSLOT); if (rc) return rc; }
+    out_off[n] = written;
+    return LZ4B200_OK;
+}
+
 int batch(lz4b200_ctx* c, const void* src, const int64_t* src_off, const int32_t* src_len, void* dst,
           const int64_t* dst_off, const int32_t* dst_cap, int32_t* out_len, int32_t n, int op, int mem, void* stream)
 {
@@ -294,6 +376,7 @@ int lz4b200_create(lz4b200_ctx** out, int device)
     cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device); c->dev.smem_optin = v;
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(&c->counters, sizeof(uint32_t) * NCOUNTER);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->hc_done, cudaEventDisableTiming);
     for (int i = 0; i < NSLOT && e == cudaSuccess; i++) {
         e = cudaStreamCreateWithFlags(&c->slot[i].stream, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->slot[i].done, cudaEventDisableTiming);
@@ -310,11 +393,12 @@ void lz4b200_destroy(lz4b200_ctx* c)
     cudaDeviceSynchronize();
     for (int i = 0; i < NSLOT; i++) {
         Slot& s = c->slot[i];
-        s.src.release(); s.dst.release(); s.meta.release(); s.hmeta.release();
+        s.src.release(); s.dst.release(); s.meta.release(); s.hmeta.release(); s.packed.release(); s.offs.release(); s.scan.release();
         if (s.done) cudaEventDestroy(s.done);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     c->hc_arena.release(); c->compact_tmp.release();
+    if (c->hc_done) cudaEventDestroy(c->hc_done);
     if (c->counters) cudaFree(c->counters);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -334,6 +418,22 @@ int lz4b200_encode_batch(lz4b200_ctx* c, const void* src, const int64_t* src_off
 {
     if (mode != LZ4B200_MODE_FAST && mode != LZ4B200_MODE_HC) return fail(LZ4B200_E_ARG, "unknown encoder mode");
     return batch(c, src, src_off, src_len, dst, dst_off, dst_cap, out_len, n, mode == LZ4B200_MODE_HC ? 1 : 0, mem, stream);
+}
+
+int lz4b200_encode_batch_packed(lz4b200_ctx* c, const void* src, const int64_t* src_off, const int32_t* src_len,
+                                const int32_t* dst_cap, void* dst, int64_t dst_total_cap, int64_t* out_off, int32_t* out_len,
+                                int32_t n, int mode)
+{
+    if (!c) return fail(LZ4B200_E_ARG, "null context");
+    if (mode != LZ4B200_MODE_FAST && mode != LZ4B200_MODE_HC) return fail(LZ4B200_E_ARG, "unknown encoder mode");
+    if (n < 0 || !out_off) return fail(LZ4B200_E_ARG, "bad argument");
+    if (n == 0) { out_off[0] = 0; return LZ4B200_OK; }
+    if (!src || !src_off || !src_len || !dst_cap || !dst || !out_len) return fail(LZ4B200_E_ARG, "null argument");
+    std::lock_guard<std::mutex> lock(c->mu);
+    DeviceGuard g(c->device);
+    if (!g.ok) return fail(LZ4B200_E_CUDA, "cudaSetDevice failed");
+    return run_host_encode_packed(c, (const uint8_t*)src, src_off, src_len, dst_cap, (uint8_t*)dst, dst_total_cap, out_off, out_len,
+                                  n, mode == LZ4B200_MODE_HC ? 1 : 0);
 }
 
 int lz4b200_decode_batch(lz4b200_ctx* c, const void* src, const int64_t* src_off, const int32_t* src_len, void* dst,
@@ -373,7 +473,11 @@ int lz4b200_set_option(lz4b200_ctx* c, const char* key, int64_t value)
     if (!c || !key) return fail(LZ4B200_E_ARG, "bad argument");
     std::lock_guard<std::mutex> lock(c->mu);
     std::string k(key);
-    if (k == "decode_lanes") { if (value != 8 && value != 16 && value != 32) return fail(LZ4B200_E_ARG, "decode_lanes must be 8, 16 or 32"); c->decode_lanes = (int)value; }
+    if (k == "decode_lanes") {
+        const int64_t g = value % 100;                 // 100 + G = the output-staged variant of the G-lane decoder
+        if ((g != 8 && g != 16 && g != 32) || (value != g && value != 100 + g)) return fail(LZ4B200_E_ARG, "decode_lanes must be 8, 16, 32 (or 100 + that)");
+        c->decode_lanes = (int)value;
+    }
     else if (k == "encode_ctas_per_sm") { if (value < 0 || value > 32) return fail(LZ4B200_E_ARG, "encode_ctas_per_sm out of range"); c->encode_ctas_per_sm = (int)value; }
     else if (k == "hc_concurrency") {
         if (value < 32 || value > (1 << 20)) return fail(LZ4B200_E_ARG, "hc_concurrency out of range");

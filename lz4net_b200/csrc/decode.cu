@@ -10,12 +10,13 @@ constexpr int DEC_THREADS = 128;
 constexpr int DEC_MIN_CTAS = 9;
 
 // Persistent CTAs; each group of G lanes pulls the next block index from a global counter.
-template <int G, bool KNOWN>
+template <int G, bool KNOWN, bool STAGED>
 __global__ void __launch_bounds__(DEC_THREADS, DEC_MIN_CTAS)
 lz4_decode_kernel(BatchArgs a, uint32_t* counter)
 {
     constexpr int GROUPS = DEC_THREADS / G;
     __shared__ DecRing<G> rings[GROUPS];
+    __shared__ DecStage<G> stages[STAGED ? GROUPS : 1];
     const int grp = threadIdx.x / G;
     const int wl = threadIdx.x & 31;                               // lane within the warp
     const int leader = wl & ~(G - 1);
@@ -35,16 +36,18 @@ lz4_decode_kernel(BatchArgs a, uint32_t* counter)
         if (st.lane == 0) b = atomicAdd(counter, 1u);
         b = simt::shfl(gmask, b, leader);
         if (b >= (uint32_t)a.n_blocks) break;
-        const int r = decode_block<G, KNOWN>(st, a.src + a.src_off[b], a.src_len[b], a.dst + a.dst_off[b], a.dst_cap[b]);
+        const int r = STAGED
+            ? decode_block_staged<G, KNOWN>(st, &stages[STAGED ? grp : 0], a.src + a.src_off[b], a.src_len[b], a.dst + a.dst_off[b], a.dst_cap[b])
+            : decode_block<G, KNOWN>(st, a.src + a.src_off[b], a.src_len[b], a.dst + a.dst_off[b], a.dst_cap[b]);
         if (st.lane == 0) a.out_len[b] = r;
     }
 }
 
-template <int G, bool KNOWN>
+template <int G, bool KNOWN, bool STAGED>
 static cudaError_t launch_one(const BatchArgs& a, uint32_t* counter, const DeviceInfo& dev, cudaStream_t stream)
 {
     int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lz4_decode_kernel<G, KNOWN>, DEC_THREADS, 0);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lz4_decode_kernel<G, KNOWN, STAGED>, DEC_THREADS, 0);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     constexpr int GROUPS = DEC_THREADS / G;
@@ -52,8 +55,15 @@ static cudaError_t launch_one(const BatchArgs& a, uint32_t* counter, const Devic
     long long grid = (long long)dev.num_sms * per_sm;
     if (grid > want) grid = want;
     if (grid < 1) grid = 1;
-    lz4_decode_kernel<G, KNOWN><<<(unsigned)grid, DEC_THREADS, 0, stream>>>(a, counter);
+    lz4_decode_kernel<G, KNOWN, STAGED><<<(unsigned)grid, DEC_THREADS, 0, stream>>>(a, counter);
     return cudaGetLastError();
+}
+
+template <int G>
+static cudaError_t launch_g(const BatchArgs& a, bool known, bool staged, uint32_t* counter, const DeviceInfo& dev, cudaStream_t stream)
+{
+    if (staged) return known ? launch_one<G, true, true>(a, counter, dev, stream) : launch_one<G, false, true>(a, counter, dev, stream);
+    return known ? launch_one<G, true, false>(a, counter, dev, stream) : launch_one<G, false, false>(a, counter, dev, stream);
 }
 
 cudaError_t launch_decode(const BatchArgs& a, bool known_len, int lanes, uint32_t* counter,
@@ -63,10 +73,11 @@ cudaError_t launch_decode(const BatchArgs& a, bool known_len, int lanes, uint32_
     cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), stream);
     if (e != cudaSuccess) return e;
     if (launches) ++*launches;
-    switch (lanes) {
-    case 8:  return known_len ? launch_one<8, true>(a, counter, dev, stream)  : launch_one<8, false>(a, counter, dev, stream);
-    case 16: return known_len ? launch_one<16, true>(a, counter, dev, stream) : launch_one<16, false>(a, counter, dev, stream);
-    default: return known_len ? launch_one<32, true>(a, counter, dev, stream) : launch_one<32, false>(a, counter, dev, stream);
+    const bool staged = lanes >= 100;            // lanes = 100 + G selects the output-staged variant
+    switch (lanes % 100) {
+    case 8:  return launch_g<8>(a, known_len, staged, counter, dev, stream);
+    case 16: return launch_g<16>(a, known_len, staged, counter, dev, stream);
+    default: return launch_g<32>(a, known_len, staged, counter, dev, stream);
     }
 }
 

@@ -228,7 +228,8 @@ SIMT_DEV int decode_block(DecStream<G>& st, const uint8_t* src, int isize, uint8
     if (isize <= 0 || cap < 0) return -1;                          // original/lz4.c:949; a block has >= 1 token
     st.begin(src, isize);
     const uint8_t* const rb = st.ring->buf;
-    uint8_t* const dl = dst + lane;                                // this lane's column of the output
+    const uint32_t rot = simt::keep(st.rot);
+    uint8_t* const dl = simt::keep(dst + lane);                    // this lane's column of the output (one register pair)
     DecCursor cur{0, 0};
     int result = 0;
     // fast path preconditions: DEC_AHEAD readable bytes after ip, and every end test of the reference trivially passes
@@ -238,7 +239,7 @@ SIMT_DEV int decode_block(DecStream<G>& st, const uint8_t* src, int isize, uint8
         if (cur.ip > in_fast) in_fast = st.window(cur.ip, isize) - DEC_AHEAD;      // slide the window (about once per chunk)
         if (cur.ip <= in_fast && cur.op <= out_fast) {
             // ---------------- fast path: the sequence header and its literals are contiguous at h ----------------
-            const uint8_t* const h = rb + (((uint32_t)cur.ip + st.rot) & (RING - 1));
+            const uint8_t* const h = rb + (((uint32_t)cur.ip + rot) & (RING - 1));
             const uint32_t token = h[0];
             uint32_t L = token >> 4, hdr = 1;
             bool simple = true;
@@ -288,6 +289,160 @@ SIMT_DEV int decode_block(DecStream<G>& st, const uint8_t* src, int isize, uint8
         const int r = decode_careful<G, KNOWN>(st, cur, isize, dst, cap, &result);
         if (r != 0) break;
     }
+    st.end();
+    return result;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Output-staged variant.  The fast path appends its output to a small per-group buffer in shared memory instead of
+// issuing byte-wide global stores; the buffer is flushed with 128-bit, 16-byte-aligned, fully coalesced stores.
+// Per-sequence global traffic drops from (litLen + matchLen) byte stores in 32/G different cache lines to 1/16 of a
+// 128-bit store per byte, and a match whose source is still staged is served from shared memory.
+//   ob index i  <->  output position ostart + i;   (dst + ostart) is 16-byte aligned;   valid bytes are [olo, ohi).
+// Everything below output position ostart + olo is in global memory and visible to the whole group (each flush and each
+// careful-path sequence ends with a group synchronisation).
+// ---------------------------------------------------------------------------------------------------------------------
+template <int G> struct DecStageGeom {
+    static constexpr int FLUSH_AT = G == 8 ? 256 : 512;            // flush once this many bytes are staged.  (A flush by one group stalls the
+                                                                   // other groups of its warp; 1 KiB for G = 8 was measured slower: it costs a third of the resident warps.)
+    static constexpr int SIZE = FLUSH_AT + 32 + 64 + 16;           // + one more fast sequence + slack
+};
+template <int G> struct alignas(16) DecStage { uint8_t ob[DecStageGeom<G>::SIZE]; };
+
+template <int G, int MAX, class LD>
+SIMT_DEV void fast_steps_smem(uint8_t* d, const uint8_t* s, uint32_t n, uint32_t lane, LD ld)
+{
+    if (lane < n) *d = ld(s);
+    if (MAX > G && n > (uint32_t)G) {
+#pragma unroll
+        for (int i = 1; i < MAX / G && i < 4; i++)
+            if (lane + i * G < n) d[i * G] = ld(s + i * G);
+        if (MAX > 4 * G && n > 4u * G) {
+#pragma unroll
+            for (int i = 4; i < MAX / G; i++)
+                if (lane + i * G < n) d[i * G] = ld(s + i * G);
+        }
+    }
+}
+
+template <int G, bool KNOWN>
+SIMT_DEV int decode_block_staged(DecStream<G>& st, DecStage<G>* stage, const uint8_t* src, int isize, uint8_t* dst, int cap)
+{
+    constexpr int RING = DecGeom<G>::RING;
+    constexpr int FAST_L = 32, FAST_M = 64;
+    constexpr int FLUSH_AT = DecStageGeom<G>::FLUSH_AT;
+    const uint32_t lane = (uint32_t)st.lane; const uint32_t gmask = st.gmask;
+    if (isize <= 0 || cap < 0) return -1;
+    st.begin(src, isize);
+    const uint8_t* const rb = st.ring->buf;
+    uint8_t* const ob = stage->ob;
+    const uint32_t rot = simt::keep(st.rot);
+    DecCursor cur{0, 0};
+    int result = 0;
+    int ostart, olo, ohi;
+    auto stage_reset = [&](int op) { const int a = (int)(((uintptr_t)dst + (uintptr_t)op) & 15); ostart = op - a; olo = ohi = a; };
+    // write out the staged bytes.  all == false: whole 16-byte vectors only, the tail (< 16 bytes) moves to the front.
+    // all == true: the tail goes out as bytes too and the stage is left empty (before the careful path / at the end).
+    auto flush = [&](bool all) {
+        simt::syncwarp(gmask);                                     // every lane's staged bytes are in place
+        uint8_t* const g = dst + ostart;
+        const int nv = ohi >> 4;
+        for (int v = (int)lane; v < nv; v += G) {
+            if (v == 0 && olo > 0) { for (int j = olo; j < 16; j++) simt::stg_u8(g + j, ob[j]); }   // first, unaligned vector
+            else simt::stg_v4(g + 16 * v, *(const uint4*)(ob + 16 * v));
+        }
+        const int done = nv << 4, rem = ohi - done;
+        const int first = done > olo ? done : olo;                 // (nv == 0: nothing was flushed, olo stays)
+        if (all) {
+            for (int j = first + (int)lane; j < ohi; j += G) simt::stg_u8(g + j, ob[j]);
+            simt::syncwarp(gmask);
+            return;
+        }
+        constexpr int TSTEPS = (15 + G) / G;                       // the tail is < 16 bytes: 1 step (G >= 16) or 2 (G = 8)
+        uint8_t t[TSTEPS];
+#pragma unroll
+        for (int i = 0; i < TSTEPS; i++) { const int j = (int)lane + i * G; t[i] = (nv > 0 && j < rem) ? ob[done + j] : (uint8_t)0; }
+        simt::syncwarp(gmask);                                     // tail read before the front is overwritten; stores ordered
+        if (nv > 0) {
+#pragma unroll
+            for (int i = 0; i < TSTEPS; i++) { const int j = (int)lane + i * G; if (j < rem) ob[j] = t[i]; }
+            ostart += done; olo = 0; ohi = rem;
+            simt::syncwarp(gmask);
+        }
+    };
+    stage_reset(0);
+    const int out_fast = cap - (FAST_L + FAST_M + 16);
+    int in_fast = st.window(0, isize) - DEC_AHEAD;
+    for (;;) {
+        if (cur.ip > in_fast) in_fast = st.window(cur.ip, isize) - DEC_AHEAD;
+        if (cur.ip <= in_fast && cur.op <= out_fast) {
+            const uint8_t* const h = rb + (((uint32_t)cur.ip + rot) & (RING - 1));
+            const uint32_t token = h[0];
+            uint32_t L = token >> 4, hdr = 1;
+            bool simple = true;
+            if (L == 15) { const uint32_t e = h[1]; L = 15 + e; hdr = 2; simple = e <= (uint32_t)(FAST_L - 15); }
+            if (simple) {
+                const uint8_t* const q = h + hdr + L;
+                const uint32_t off = q[0] | ((uint32_t)q[1] << 8);
+                uint32_t M = token & 15, adv = hdr + L + 2;
+                if (M == 15) { const uint32_t e = q[2]; M = 15 + e; adv++; simple = e <= (uint32_t)(FAST_M - 19); }
+                M += 4;
+                if (simple) {
+                    const uint32_t opl = (uint32_t)cur.op + L;
+                    if (off - 1u >= opl) { result = -(cur.ip + (int)adv) - 1; break; }            // :863 / :983
+                    const uint8_t* const lit = h + hdr;
+                    auto lds = [](const uint8_t* p) { return *p; };
+                    uint8_t* const o = ob + ohi;                   // == staged image of output position cur.op
+                    fast_steps_smem<G, FAST_L>(o + lane, lit + lane, L, lane, lds);
+                    uint8_t* const mo = o + L;
+                    const uint32_t span = off < M ? off : M;       // distinct source bytes
+                    if (off <= L) {
+                        // source inside this sequence's own literals: still in the input ring, no ordering needed
+                        const uint8_t* const s = lit + (L - off);
+                        if (off >= M) fast_steps_smem<G, FAST_M>(mo + lane, s + lane, M, lane, lds);
+                        else {
+                            const float rcp = 1.0f / (float)off;
+#pragma unroll 1
+                            for (uint32_t k = lane; k < M; k += G) mo[k] = s[small_mod(k, off, rcp)];
+                        }
+                    } else {
+                        const int spos = (int)opl - (int)off;      // output position of the first source byte
+                        const int glim = ostart + olo;             // positions below are in global memory, visible
+                        if (spos + (int)span <= glim) {
+                            const uint8_t* const s = dst + spos;
+                            auto ldg = [](const uint8_t* p) { return simt::ldg_u8(p); };
+                            if (off >= M) fast_steps_smem<G, FAST_M>(mo + lane, s + lane, M, lane, ldg);
+                            else {
+                                const float rcp = 1.0f / (float)off;
+#pragma unroll 1
+                                for (uint32_t k = lane; k < M; k += G) mo[k] = simt::ldg_u8(s + small_mod(k, off, rcp));
+                            }
+                        } else {
+                            // (partly) staged source: bytes other lanes wrote in this or earlier sequences
+                            simt::syncwarp(gmask);
+                            const float rcp = 1.0f / (float)off;
+#pragma unroll 1
+                            for (uint32_t k = lane; k < M; k += G) {
+                                const int p = spos + (int)(off >= M ? k : small_mod(k, off, rcp));
+                                mo[k] = p >= glim ? ob[p - ostart] : simt::ldg_u8(dst + p);
+                            }
+                        }
+                    }
+                    ohi += (int)(L + M);
+                    cur.ip += (int)adv; cur.op = (int)(opl + M);
+                    if (ohi > FLUSH_AT) flush(false);
+                    continue;
+                }
+            }
+        }
+        // ---------------- careful path: works on global memory directly ----------------
+        flush(true);
+        const int r = decode_careful<G, KNOWN>(st, cur, isize, dst, cap, &result);
+        if (r != 0) { ohi = olo; break; }
+        simt::syncwarp(gmask);                                     // its stores are visible before anything reads them back
+        stage_reset(cur.op);
+    }
+    if (ohi > olo) flush(true);
     st.end();
     return result;
 }

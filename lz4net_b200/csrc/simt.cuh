@@ -26,6 +26,11 @@ SIMT_DEV int clz(uint32_t v) { return __clz((int)v); }
 SIMT_DEV int popc(uint32_t v) { return __popc(v); }
 SIMT_DEV uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) { return __funnelshift_r(lo, hi, sh); }
 
+// Opaque identity: stops the compiler from re-deriving a value from its parts at every use (e.g. a 64-bit pointer
+// that it would otherwise rebuild from base + offset + lane on each store).
+template <class T> SIMT_DEV T* keep(T* p) { asm volatile("" : "+l"(p)); return p; }
+SIMT_DEV uint32_t keep(uint32_t v) { asm volatile("" : "+r"(v)); return v; }
+
 // coherent loads (data this kernel wrote earlier: decoder back-references): plain ld.global, L1-cacheable.  They are
 // always separated from the producing store of another lane by a __syncwarp(), which is a memory barrier for the
 // compiler as well, so no asm/volatile is needed (and plain loads can be predicated instead of branched around).

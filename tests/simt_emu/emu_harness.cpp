@@ -15,12 +15,18 @@ namespace {
 struct DecJob {
     int G; bool known; int nblocks;
     const uint8_t* const* src; const int* isize; uint8_t* const* dst; const int* cap; int* result;
+    bool staged;
     DecRing<32> r32[1]; DecRing<16> r16[2]; DecRing<8> r8[4];
+    DecStage<32> s32[1]; DecStage<16> s16[2]; DecStage<8> s8[4];
+    template <int G> DecStage<G>* stages();
     template <int G> DecRing<G>* rings();
 };
 template <> DecRing<32>* DecJob::rings<32>() { return r32; }
 template <> DecRing<16>* DecJob::rings<16>() { return r16; }
 template <> DecRing<8>*  DecJob::rings<8>()  { return r8; }
+template <> DecStage<32>* DecJob::stages<32>() { return s32; }
+template <> DecStage<16>* DecJob::stages<16>() { return s16; }
+template <> DecStage<8>*  DecJob::stages<8>()  { return s8; }
 
 template <int G, bool KNOWN>
 void dec_lane(int wl, DecJob* j)
@@ -33,7 +39,8 @@ void dec_lane(int wl, DecJob* j)
     st.gbase = 0;
     // every group walks the block list with a stride, like the kernel's dynamic hand-out
     for (int b = grp; b < j->nblocks; b += 32 / G) {
-        int r = decode_block<G, KNOWN>(st, j->src[b], j->isize[b], j->dst[b], j->cap[b]);
+        int r = j->staged ? decode_block_staged<G, KNOWN>(st, &j->stages<G>()[grp], j->src[b], j->isize[b], j->dst[b], j->cap[b])
+                          : decode_block<G, KNOWN>(st, j->src[b], j->isize[b], j->dst[b], j->cap[b]);
         if (st.lane == 0) j->result[b] = r;
     }
 }
@@ -70,6 +77,7 @@ void emu_decode(int G, int known, int nblocks, const uint8_t* const* src, const 
                 uint8_t* const* dst, const int* cap, int* result, uint64_t sched_seed)
 {
     DecJob* j = new DecJob();
+    j->staged = G >= 100; G %= 100;
     j->G = G; j->known = known != 0; j->nblocks = nblocks; j->src = src; j->isize = isize; j->dst = dst; j->cap = cap; j->result = result;
     simt_emu::run_warp(dec_entry, j, sched_seed);
     delete j;

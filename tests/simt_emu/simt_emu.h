@@ -34,6 +34,8 @@ static inline int clz(uint32_t v) { return v ? __builtin_clz(v) : 32; }
 static inline int popc(uint32_t v) { return __builtin_popcount(v); }
 static inline uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) { uint64_t t = ((uint64_t)hi << 32) | lo; return (uint32_t)(t >> (sh & 31)); }
 
+template <class T> static inline T* keep(T* p) { return p; }
+static inline uint32_t keep(uint32_t v) { return v; }
 static inline uint8_t  ldg_u8(const uint8_t* p) { return *p; }
 static inline uint32_t ldg_u32(const void* p) { uint32_t v; memcpy(&v, p, 4); return v; }
 static inline uint4    ldg_v4(const void* p) { uint4 v; memcpy(&v, p, 16); return v; }

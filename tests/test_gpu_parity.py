@@ -87,7 +87,7 @@ def test_golden_vectors(ctx):
             assert r2 == c[mode]["len_cap_n"], (c["name"], mode)
 
 
-@pytest.mark.parametrize("lanes", [32, 16, 8])
+@pytest.mark.parametrize("lanes", [32, 16, 8, 132, 116, 108])
 @pytest.mark.parametrize("known", [True, False])
 def test_decode_bit_exact(ctx, lanes, known):
     ctx.set_option("decode_lanes", lanes)
@@ -96,7 +96,7 @@ def test_decode_bit_exact(ctx, lanes, known):
     for i, d in enumerate(raws):
         comp.append((oracle.encode_hc if i % 3 == 0 else oracle.encode)(d)[1])
     res, outs = ctx.decode_blocks(comp, [len(d) for d in raws], known=known)
-    ctx.set_option("decode_lanes", 32)
+    ctx.set_option("decode_lanes", 16)
     for c, d, r, o in zip(comp, raws, res, outs):
         assert r == (len(c) if known else len(d)), (len(d), r)
         assert o == d
@@ -362,3 +362,39 @@ def test_lz4stream_class_random_writes_and_reads(ctx, hc):
             assert bytes(back) == data
         with pytest.raises(EOFError):
             LZ4Stream(io.BytesIO(wire[:-2]), LZ4StreamMode.Decompress, context=ctx).Read(len(data) + 1)
+
+
+@pytest.mark.parametrize("hc", [False, True])
+def test_encode_batch_packed(ctx, hc):
+    """Packed host output: same per-block bytes and return values as the slot form, laid back to back in block order;
+    a block that does not fit its cap contributes nothing.  Small chunks force the multi-chunk pipeline."""
+    fn = oracle.encode_hc if hc else oracle.encode
+    blocks = _inputs(lens=[65536, 3000, 0, 13, 40000, 65546])
+    caps = []
+    for i, b in enumerate(blocks):
+        r = fn(b)[0]
+        caps.append([oracle.bound(len(b)), len(b), r, max(r - 1, 0)][i % 4])
+    ctx.set_option("host_chunk_mb", 1)
+    try:
+        res, off, packed = ctx.encode_blocks_packed(blocks, caps=caps, hc=hc)
+    finally:
+        ctx.set_option("host_chunk_mb", 256)
+    pos = 0
+    for b, c, r, o in zip(blocks, caps, res, off):
+        er, eo = fn(b, cap=c)
+        assert r == er and o == pos, (len(b), c)
+        assert packed[o:o + max(r, 0)] == eo
+        pos += max(r, 0)
+    assert off[-1] == pos == len(packed)
+
+
+def test_hc_host_batch_many_small_chunks(ctx):
+    """Regression: HC launches of different pipeline stages share one state arena and must not overlap."""
+    blocks = [cases.content(m, 65536, seed=70 + i).tobytes() for i, m in enumerate(cases.MODELS * 3)]
+    ctx.set_option("host_chunk_mb", 1)
+    try:
+        res, outs = ctx.encode_blocks(blocks, hc=True)
+    finally:
+        ctx.set_option("host_chunk_mb", 256)
+    for b, r, o in zip(blocks, res, outs):
+        assert (r, o) == oracle.encode_hc(b)

@@ -74,7 +74,7 @@ def test_encode_schedule_independent():
         _enc_check(blocks, sched_seed=seed)
 
 
-@pytest.mark.parametrize("lanes", [32, 16, 8])
+@pytest.mark.parametrize("lanes", [32, 16, 8, 132, 116, 108])
 @pytest.mark.parametrize("known", [True, False])
 def test_decode_matches_oracle(lanes, known):
     blocks, raws = [], []
@@ -89,7 +89,7 @@ def test_decode_matches_oracle(lanes, known):
         assert o == d
 
 
-@pytest.mark.parametrize("lanes", [32, 8])
+@pytest.mark.parametrize("lanes", [32, 8, 116])
 def test_decode_size_invariants(lanes):
     """fuzzer.c:176-210 -- exact size works; size +-1 fails; verdicts equal the oracle's (which is pinned to the reference)."""
     from lz4net_b200 import synth
@@ -130,6 +130,9 @@ def test_decode_corrupt_streams_never_escape(known):
             c[int(rng.integers(0, len(c)))] = 0xFF
         comp.append(bytes(c)); caps.append(len(d))
     res, outs = emu.decode(comp, caps, lanes=32, known=known, sched_seed=13)
+    res2, outs2 = emu.decode(comp, caps, lanes=108, known=known, sched_seed=14)       # output-staged variant, 8 lanes
+    assert [r < 0 for r in res2] == [r < 0 for r in res] and [r for r in res2 if r >= 0] == [r for r in res if r >= 0]
+    assert [o for r, o in zip(res2, outs2) if r >= 0] == [o for r, o in zip(res, outs) if r >= 0]
     for c, cap, r, o in zip(comp, caps, res, outs):
         er, eo = (oracle.decode_known if known else oracle.decode_unknown)(c, cap)
         assert (r < 0) == (er < 0), (r, er)
@@ -141,8 +144,9 @@ def test_decode_corrupt_streams_never_escape(known):
 def test_decode_unaligned_stream_start(skew):
     raws = [cases.content(m, 9000, seed=skew).tobytes() for m in cases.MODELS]
     comp = [oracle.encode(d)[1] for d in raws]
-    res, outs = emu.decode(comp, [len(d) for d in raws], lanes=16, known=True, sched_seed=skew, src_skew=skew)
-    assert outs == raws and res == [len(c) for c in comp]
+    for lanes in (16, 116, 108):
+        res, outs = emu.decode(comp, [len(d) for d in raws], lanes=lanes, known=True, sched_seed=skew, src_skew=skew)
+        assert outs == raws and res == [len(c) for c in comp]
 
 
 def test_decode_long_overlapping_matches():
@@ -153,6 +157,6 @@ def test_decode_long_overlapping_matches():
         pat = rng.integers(0, 256, off, dtype=np.uint8)
         raws.append(np.tile(pat, 9000 // off + 2)[:9000].tobytes())
     comp = [oracle.encode(d)[1] for d in raws]
-    for lanes in (32, 16, 8):
+    for lanes in (32, 16, 8, 132, 116, 108):
         res, outs = emu.decode(comp, [len(d) for d in raws], lanes=lanes, known=True, sched_seed=lanes)
         assert outs == raws

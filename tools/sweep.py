@@ -16,7 +16,8 @@ for cls in CLASSES:
     w = Workload(ctx, nb, cls, nb, seed=2)
     cs = w.verify(); rb = nb * BLOCK
     row = {"ratio": round(cs / rb, 4)}
-    for lanes in (32, 16, 8):
+    LANES = [int(x) for x in sys.argv[4].split(",")] if len(sys.argv) > 4 else (32, 16, 8, 132, 116, 108)
+    for lanes in LANES:
         ctx.set_option("decode_lanes", lanes)
         # correctness under this lane count
         for wv in range(w.n_waves):
