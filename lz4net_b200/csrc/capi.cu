@@ -79,7 +79,8 @@ struct lz4b200_ctx {
     int next_counter = 0;
     DevBuf hc_arena, compact_tmp;
     cudaEvent_t hc_done = nullptr;         // the HC state arena is shared: HC launches are chained through this event
-    int decode_lanes = 16;
+    int decode_lanes = 16;                 // lanes per block for device-memory batches (+100 = output-staged variant)
+    bool decode_lanes_auto = true;         // host-memory batches: chosen per chunk from the compression ratio
     int encode_ctas_per_sm = 0;            // 0 = as many as shared memory allows
     size_t host_chunk_bytes = HOST_CHUNK_BYTES_DEFAULT;
     int hc_concurrency = 65536;          // blocks in flight (one thread each, 256 KiB state): measured 3x over 16384
@@ -98,8 +99,13 @@ struct DeviceGuard {
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
-int run_device(lz4b200_ctx* c, const BatchArgs& a, int op /*0 enc fast, 1 enc hc, 2 dec known, 3 dec unknown*/, cudaStream_t st)
+// Decode group size from the ratio compressed/raw of a batch (tools/sweep.py): incompressible data is long literal runs
+// (whole warps, 128-bit copies), nearly-empty streams are long matches, everything between is sequence-dense.
+int lanes_for_ratio(double ratio) { return ratio > 0.95 ? 32 : (ratio < 0.05 ? 16 : 108); }
+
+int run_device(lz4b200_ctx* c, const BatchArgs& a, int op /*0 enc fast, 1 enc hc, 2 dec known, 3 dec unknown*/, cudaStream_t st, int lanes = 0)
 {
+    if (!lanes) lanes = c->decode_lanes;
     cudaError_t e = cudaSuccess;
     switch (op) {
     case 0: e = launch_encode_fast(a, c->counter(), c->encode_ctas_per_sm, c->dev, st, &c->launches); break;
@@ -116,8 +122,8 @@ int run_device(lz4b200_ctx* c, const BatchArgs& a, int op /*0 enc fast, 1 enc hc
         if (e == cudaSuccess) e = cudaEventRecord(c->hc_done, st);
         break;
     }
-    case 2: e = launch_decode(a, true, c->decode_lanes, c->counter(), c->dev, st, &c->launches); break;
-    default: e = launch_decode(a, false, c->decode_lanes, c->counter(), c->dev, st, &c->launches); break;
+    case 2: e = launch_decode(a, true, lanes, c->counter(), c->dev, st, &c->launches); break;
+    default: e = launch_decode(a, false, lanes, c->counter(), c->dev, st, &c->launches); break;
     }
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
     return LZ4B200_OK;
@@ -194,7 +200,13 @@ int run_host(lz4b200_ctx* c, const uint8_t* src, const int64_t* src_off, const i
         a.src_off = (const int64_t*)d_meta; a.dst_off = a.src_off + m;
         a.src_len = (const int32_t*)(a.dst_off + m); a.dst_cap = a.src_len + m;
         a.out_len = (int32_t*)(a.dst_cap + m); a.n_blocks = m;
-        rc = run_device(c, a, op, sl.stream); if (rc) return rc;
+        int lanes = 0;
+        if (decode && c->decode_lanes_auto) {
+            double cs = 0, rs = 0;
+            for (int32_t i = b0; i < b1; i++) { cs += src_len[i]; rs += dst_cap[i]; }
+            lanes = lanes_for_ratio(rs > 0 ? cs / rs : 1.0);
+        }
+        rc = run_device(c, a, op, sl.stream, lanes); if (rc) return rc;
         CU(cudaMemcpyAsync(h_out, a.out_len, sizeof(int32_t) * (size_t)m, cudaMemcpyDeviceToHost, sl.stream));
         if (contiguous) {
             int32_t r0 = b0;
@@ -476,8 +488,9 @@ int lz4b200_set_option(lz4b200_ctx* c, const char* key, int64_t value)
     if (k == "decode_lanes") {
         const int64_t g = value % 100;                 // 100 + G = the output-staged variant of the G-lane decoder
         if ((g != 8 && g != 16 && g != 32) || (value != g && value != 100 + g)) return fail(LZ4B200_E_ARG, "decode_lanes must be 8, 16, 32 (or 100 + that)");
-        c->decode_lanes = (int)value;
+        c->decode_lanes = (int)value; c->decode_lanes_auto = false;
     }
+    else if (k == "decode_lanes_auto") { c->decode_lanes_auto = value != 0; }
     else if (k == "encode_ctas_per_sm") { if (value < 0 || value > 32) return fail(LZ4B200_E_ARG, "encode_ctas_per_sm out of range"); c->encode_ctas_per_sm = (int)value; }
     else if (k == "hc_concurrency") {
         if (value < 32 || value > (1 << 20)) return fail(LZ4B200_E_ARG, "hc_concurrency out of range");
