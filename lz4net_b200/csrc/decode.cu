@@ -10,8 +10,9 @@ constexpr int DEC_THREADS = 128;
 constexpr int DEC_MIN_CTAS = 9;
 
 // Persistent CTAs; each group of G lanes pulls the next block index from a global counter.
+// (the staged sub-warp variants are limited to 8 CTAs per SM by shared memory anyway: let them have 64 registers)
 template <int G, bool KNOWN, bool STAGED>
-__global__ void __launch_bounds__(DEC_THREADS, DEC_MIN_CTAS)
+__global__ void __launch_bounds__(DEC_THREADS, (STAGED && G < 32) ? 8 : DEC_MIN_CTAS)
 lz4_decode_kernel(BatchArgs a, uint32_t* counter)
 {
     constexpr int GROUPS = DEC_THREADS / G;

@@ -240,17 +240,17 @@ SIMT_DEV int decode_block(DecStream<G>& st, const uint8_t* src, int isize, uint8
         if (cur.ip <= in_fast && cur.op <= out_fast) {
             // ---------------- fast path: the sequence header and its literals are contiguous at h ----------------
             const uint8_t* const h = rb + (((uint32_t)cur.ip + rot) & (RING - 1));
-            const uint32_t token = h[0];
-            uint32_t L = token >> 4, hdr = 1;
-            bool simple = true;
-            if (L == 15) { const uint32_t e = h[1]; L = 15 + e; hdr = 2; simple = e <= (uint32_t)(FAST_L - 15); }
-            if (simple) {
+            // branch-free header parse: both possible length bytes are loaded unconditionally (they are inside the
+            // 64-byte window either way) and selected, so the loads of one header overlap instead of chaining
+            const uint32_t token = h[0], e1 = h[1];
+            const bool lx = (token >> 4) == 15;
+            const uint32_t L = lx ? 15 + e1 : token >> 4, hdr = lx ? 2u : 1u;
+            if (L <= (uint32_t)FAST_L) {                            // (an e1 of 255 gives L >= 270 and falls to the careful path)
                 const uint8_t* const q = h + hdr + L;
-                const uint32_t off = q[0] | ((uint32_t)q[1] << 8);
-                uint32_t M = token & 15, adv = hdr + L + 2;
-                if (M == 15) { const uint32_t e = q[2]; M = 15 + e; adv++; simple = e <= (uint32_t)(FAST_M - 19); }
-                M += 4;
-                if (simple) {
+                const uint32_t off = q[0] | ((uint32_t)q[1] << 8), e2 = q[2];
+                const bool mx = (token & 15) == 15;
+                const uint32_t M = (mx ? 15 + e2 : token & 15) + 4, adv = hdr + L + (mx ? 3u : 2u);
+                if (M <= (uint32_t)FAST_M) {                        // (255 -> M >= 274 -> careful path)
                     const uint32_t opl = (uint32_t)cur.op + L;
                     if (off - 1u >= opl) { result = -(cur.ip + (int)adv) - 1; break; }            // :863 / :983 (0 or too far)
                     uint8_t* const d = dl + cur.op;
@@ -377,17 +377,17 @@ SIMT_DEV int decode_block_staged(DecStream<G>& st, DecStage<G>* stage, const uin
         if (cur.ip > in_fast) in_fast = st.window(cur.ip, isize) - DEC_AHEAD;
         if (cur.ip <= in_fast && cur.op <= out_fast) {
             const uint8_t* const h = rb + (((uint32_t)cur.ip + rot) & (RING - 1));
-            const uint32_t token = h[0];
-            uint32_t L = token >> 4, hdr = 1;
-            bool simple = true;
-            if (L == 15) { const uint32_t e = h[1]; L = 15 + e; hdr = 2; simple = e <= (uint32_t)(FAST_L - 15); }
-            if (simple) {
+            // branch-free header parse: both possible length bytes are loaded unconditionally (they are inside the
+            // 64-byte window either way) and selected, so the loads of one header overlap instead of chaining
+            const uint32_t token = h[0], e1 = h[1];
+            const bool lx = (token >> 4) == 15;
+            const uint32_t L = lx ? 15 + e1 : token >> 4, hdr = lx ? 2u : 1u;
+            if (L <= (uint32_t)FAST_L) {                            // (an e1 of 255 gives L >= 270 and falls to the careful path)
                 const uint8_t* const q = h + hdr + L;
-                const uint32_t off = q[0] | ((uint32_t)q[1] << 8);
-                uint32_t M = token & 15, adv = hdr + L + 2;
-                if (M == 15) { const uint32_t e = q[2]; M = 15 + e; adv++; simple = e <= (uint32_t)(FAST_M - 19); }
-                M += 4;
-                if (simple) {
+                const uint32_t off = q[0] | ((uint32_t)q[1] << 8), e2 = q[2];
+                const bool mx = (token & 15) == 15;
+                const uint32_t M = (mx ? 15 + e2 : token & 15) + 4, adv = hdr + L + (mx ? 3u : 2u);
+                if (M <= (uint32_t)FAST_M) {                        // (255 -> M >= 274 -> careful path)
                     const uint32_t opl = (uint32_t)cur.op + L;
                     if (off - 1u >= opl) { result = -(cur.ip + (int)adv) - 1; break; }            // :863 / :983
                     const uint8_t* const lit = h + hdr;
