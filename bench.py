@@ -381,11 +381,21 @@ def main():
     enc_gbs = total_raw / t_enc / GB; dec_gbs = total_raw / t_dec / GB
     # roofline (per GPU): algorithmic bytes = raw + compressed, both directions of each kernel
     alg = (total_raw + csum_all) / world
+    # DRAM traffic per launch from the committed ncu --set full capture (per-block bytes x blocks in the launch); only
+    # meaningful for the class it was captured on
+    traffic_dec = traffic_enc = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        if args.cls == "E50":
+            traffic_dec = int(tj["lz4_decode_kernel"]["dram_bytes"] / tj["blocks"] * min(args.wave, args.blocks))
+            traffic_enc = int(tj["lz4_encode_fast_kernel"]["dram_bytes"] / tj["blocks"] * args.blocks)
+    except Exception:
+        pass
     roof_dec = {"kernel": "lz4_decode_kernel", "bound": "hbm", "achieved": round(alg / t_dec / GB, 1), "peak": peak_hbm, "unit": "GB/s",
-                "frac": round(alg / t_dec / GB / peak_hbm, 4), "traffic": None, "peak_source": peak_src,
+                "frac": round(alg / t_dec / GB / peak_hbm, 4), "traffic": traffic_dec, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": int(alg / nw), "launch_ms": round(t_dec / nw * 1e3, 3)}
     roof_enc = {"kernel": "lz4_encode_fast_kernel", "bound": "hbm", "achieved": round(alg / t_enc / GB, 1), "peak": peak_hbm, "unit": "GB/s",
-                "frac": round(alg / t_enc / GB / peak_hbm, 4), "traffic": None, "peak_source": peak_src,
+                "frac": round(alg / t_enc / GB / peak_hbm, 4), "traffic": traffic_enc, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": int(alg), "launch_ms": round(t_enc * 1e3, 3)}
 
     # ---- end to end through the C ABI with host buffers (every rank, concurrently) -----------------------------------

@@ -11,7 +11,7 @@ ctx = lz4net_b200.Context(0)
 peak = 6587.0
 res = {}
 CLASSES = sys.argv[2].split(",") if len(sys.argv) > 2 else ("E0", "E50", "E100", "ETEXT")
-ENC = len(sys.argv) <= 3
+ENC = len(sys.argv) <= 3 or sys.argv[3] == "enc"
 for cls in CLASSES:
     w = Workload(ctx, nb, cls, nb, seed=2)
     cs = w.verify(); rb = nb * BLOCK
@@ -34,7 +34,7 @@ for cls in CLASSES:
         t = sorted(ts)[len(ts) // 2]
         row[f"dec{lanes}_gbs"] = round(rb / t / GB, 1); row[f"dec{lanes}_frac"] = round((rb + cs) / t / GB / peak, 3)
     ctx.set_option("decode_lanes", 32)
-    for ctas in ((0, 8, 4) if ENC else ()):
+    for ctas in ((0,) if ENC else ()):
         ctx.set_option("encode_ctas_per_sm", ctas)
         ts = []
         for _ in range(3):
