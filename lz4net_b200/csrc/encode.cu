@@ -7,8 +7,11 @@ namespace lz4b200 {
 
 // ---- fast encoder: one warp (= one CTA) per block, persistent, dynamic block hand-out --------------------------------
 // The position table is dynamic shared memory so the launcher can also use its size to pin the number of CTAs per SM.
-__global__ void __launch_bounds__(32)
-lz4_encode_fast_kernel(BatchArgs a, uint32_t* counter)
+// (min 16 CTAs per SM only tells ptxas how many registers it may use: 128.  With the bare bound it assumes the
+// hardware maximum of 32 CTAs, caps the kernel at 64 registers and spills; shared memory allows 13 CTAs anyway.)
+template <int DUP, int LDP>
+__global__ void __launch_bounds__(32, 16)
+lz4_encode_fast_kernel(BatchArgs a, uint32_t* counter, EncTune tune)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     EncShared* sh = (EncShared*)smem;
@@ -18,12 +21,21 @@ lz4_encode_fast_kernel(BatchArgs a, uint32_t* counter)
         if (lane == 0) b = atomicAdd(counter, 1u);
         b = simt::shfl(0xFFFFFFFFu, b, 0);
         if (b >= (uint32_t)a.n_blocks) break;
-        const int r = encode_block(sh, a.src + a.src_off[b], a.src_len[b], a.dst + a.dst_off[b], a.dst_cap[b], lane);
+        const int r = encode_block<DUP, LDP>(sh, a.src + a.src_off[b], a.src_len[b], a.dst + a.dst_off[b], a.dst_cap[b], lane, tune);
         if (lane == 0) a.out_len[b] = r;
     }
 }
 
-cudaError_t launch_encode_fast(const BatchArgs& a, uint32_t* counter, int ctas_per_sm,
+template <int DUP, int LDP>
+static cudaError_t launch_fast_t(const BatchArgs& a, uint32_t* counter, int dyn, long long grid, int prefetch, cudaStream_t stream)
+{
+    cudaError_t e = cudaFuncSetAttribute(lz4_encode_fast_kernel<DUP, LDP>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+    if (e != cudaSuccess) return e;
+    lz4_encode_fast_kernel<DUP, LDP><<<(unsigned)grid, 32, dyn, stream>>>(a, counter, EncTune{prefetch});
+    return cudaGetLastError();
+}
+
+cudaError_t launch_encode_fast(const BatchArgs& a, uint32_t* counter, int ctas_per_sm, int prefetch, int variant,
                                const DeviceInfo& dev, cudaStream_t stream, int64_t* launches)
 {
     if (a.n_blocks <= 0) return cudaSuccess;
@@ -35,15 +47,18 @@ cudaError_t launch_encode_fast(const BatchArgs& a, uint32_t* counter, int ctas_p
     dyn &= ~1023;
     if (dyn > dev.smem_optin) dyn = dev.smem_optin & ~1023;
     if (dyn < (int)sizeof(EncShared)) dyn = (int)sizeof(EncShared);
-    cudaError_t e = cudaFuncSetAttribute(lz4_encode_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
-    if (e != cudaSuccess) return e;
-    e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), stream);
+    cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), stream);
     if (e != cudaSuccess) return e;
     long long grid = (long long)dev.num_sms * ctas_per_sm;
     if (grid > a.n_blocks) grid = a.n_blocks;
-    lz4_encode_fast_kernel<<<(unsigned)grid, 32, dyn, stream>>>(a, counter);
     if (launches) ++*launches;
-    return cudaGetLastError();
+    switch (variant) {                      // variant % 10: how same-hash iterations of one round are found (lz4_encode.cuh);
+                                            // variant / 10: candidate loads through L1 (0) or L2 only (1)
+    case 1:  return launch_fast_t<1, 0>(a, counter, dyn, grid, prefetch, stream);  // always exact: one vote per hash bit
+    case 11: return launch_fast_t<1, 1>(a, counter, dyn, grid, prefetch, stream);
+    case 12: return launch_fast_t<2, 1>(a, counter, dyn, grid, prefetch, stream);
+    default: return launch_fast_t<2, 0>(a, counter, dyn, grid, prefetch, stream);  // through the table, pairs resolved in place
+    }
 }
 
 // ---- HC encoder: one THREAD per block, state arena in global memory -------------------------------------------------

@@ -52,6 +52,20 @@ struct InWords {
         const uint32_t hi = sh ? simt::ldg_nc_u32(w + i + 1) : 0u;
         return simt::funnel_r(lo, hi, sh);
     }
+    // The same read split in two, so that the caller decides where the warp waits for the data: raw() issues the loads
+    // (POLICY 0: read-only path through L1; 1: L2 only -- for probes at random earlier positions, which would otherwise
+    // evict the forward window from L1), word() assembles the value.
+    struct Raw { uint32_t lo, hi, sh; };
+    template <int POLICY>
+    SIMT_MEM Raw raw(int p) const
+    {
+        const uint32_t q = (uint32_t)p + sk, i = q >> 2;
+        Raw r; r.sh = (q & 3u) * 8u;
+        if (POLICY == 1) { r.lo = simt::ldg_cg_u32(w + i); r.hi = simt::ldg_cg_u32(w + i + 1); }
+        else             { r.lo = simt::ldg_nc_u32(w + i); r.hi = simt::ldg_nc_u32(w + i + 1); }
+        return r;
+    }
+    static SIMT_MEM uint32_t word(const Raw& r) { return simt::funnel_r(r.lo, r.hi, r.sh); }
 };
 
 // ---- source policies -------------------------------------------------------------------------------------------

@@ -4,18 +4,33 @@
 // src/LZ4ps/LZ4Codec.Safe64.Dirty.cs:306-527) for inputs < 65547 bytes and LZ4_compressCtx (original/lz4.c:345-562;
 // Safe64.Dirty.cs:77-300) above that, behind the LZ4_compress_limitedOutput dispatch (original/lz4.c:774-792).
 // The emitted bytes must equal lz4net's LZ4Codec.Encode, so the greedy parse is reproduced exactly -- but as a
-// warp-wide formulation of the serial state machine:
+// warp-wide formulation of the serial state machine, split in two phases:
 //
-//   * one "round" evaluates 32 consecutive probe positions of the reference's find-match loop at once: the probe
+// PARSE (the serial dependency chain, kept as short as it can be):
+//   * one "round" evaluates 32 consecutive iterations of the reference's find-match loop at once: the probe
 //     positions follow from the attempt counter alone (step = attempts >> 6, :636/:644), their hashes only depend on
 //     the input, and the table state each serial iteration would have seen is reconstructed inside the round with
 //     MATCH.ANY (a lower lane with the same hash supplies the candidate instead of the table);
 //   * VOTE + FFS picks the first lane that either hits or runs past mflimit (:648); only lanes up to it commit their
 //     table update, highest lane per bucket winning -- exactly the serial write order;
-//   * the backward catch-up (:657), the match-length count (:701-716) and all copies are lane-parallel.
+//   * the two table operations that follow every match (insert ip-2, probe+insert ip, :739-751) are not a separate
+//     step: they ride in lanes 0 and 1 of the next round ("fused round"), whose remaining 30 lanes are the first 30
+//     iterations of the find-match loop that starts at ip+1.  A hit in lane 1 is the reference's zero-literal
+//     `goto _next_match`;
+//   * the backward catch-up (:657) and the forward match-length count (:701-716) are independent once (ip, ref) are
+//     known: their loads are issued together, before the first vote;
+//   * nothing is written during the parse: each found sequence is one record (anchor, literal length, offset, match
+//     length) parked in the registers of one lane.
+// EMIT (every 32 sequences, fully lane-parallel):
+//   * sizes -> warp prefix sum -> every sequence's output position; the reference's output-limit checks (:663, :728,
+//     :762) are evaluated for all 32 sequences at once from those positions;
+//   * lane k writes token, length bytes and offset of sequence k; literal runs are copied by the whole warp, four
+//     short runs per step.
 //
 // The 16 KiB position table (u16[8192] for the 64 K variant, u32[4096] for the general one -- the same footprint)
-// lives in shared memory, zero-filled per block (zero == "candidate at position 0", :583/:651).
+// lives in shared memory, zero-filled per block (zero == "candidate at position 0", :583/:651).  The input is read
+// through the read-only path; the lines ahead of the cursor are software-prefetched (the parse is a latency chain:
+// a cold miss on the forward stream would stall it for a full DRAM round trip per 128 bytes).
 #pragma once
 #include "simt.cuh"
 #include "lz4_copy.cuh"
@@ -26,179 +41,403 @@ struct alignas(16) EncShared { uint32_t table[4096]; };
 
 constexpr int LZ4_64KLIMIT = 65547;                                // original/lz4.c:565
 
-// token length extension: `v` as a run of 255s plus a remainder byte, written lane-parallel; returns bytes written
-SIMT_DEV int put_len_ext(uint8_t* dst, int op, int cap, int v, int lane)
+struct EncTune { int pf_dist; };                                   // > 0: L1 prefetch that many bytes ahead; < 0: L2; 0: off
+
+// flags kept above the 16-bit offset of a parked sequence
+constexpr uint32_t SEQ_NOCHK = 0x10000u;                           // zero-literal `goto _next_match` sequence: no :663 check
+constexpr uint32_t SEQ_LAST  = 0x20000u;                           // the last literal run (no match part)
+
+// Lanes whose hash equals mine (bit mask, always contains me): one vote per hash bit.  Invalid lanes match nobody.
+template <int BITS>
+SIMT_DEV uint32_t hash_peers(uint32_t h, bool valid, uint32_t vmask, int lane)
 {
-    if (v < 255) {                                                 // the common case: one byte
-        if (lane == 0 && op < cap) simt::stg_u8(dst + op, (uint8_t)v);
-        return 1;
+    uint32_t m = vmask;
+#pragma unroll
+    for (int b = 0; b < BITS; b++) {
+        const uint32_t v = simt::ballot(0xFFFFFFFFu, (h >> b) & 1u);
+        m &= ((h >> b) & 1u) ? v : ~v;
     }
-    const int nff = v / 255;
-    for (int i = lane; i < nff; i += 32) if (op + i < cap) simt::stg_u8(dst + op + i, 255);
-    if (lane == 0 && op + nff < cap) simt::stg_u8(dst + op + nff, (uint8_t)(v - nff * 255));
-    return nff + 1;
+    return valid ? m : (1u << lane);
 }
 
+// The position table behind a 32-bit shared-window address.
 template <bool GENERAL>
-SIMT_DEV int encode_block_t(EncShared* sh, const uint8_t* src, int n, uint8_t* dst, int cap, int lane)
+struct EncTable {
+    simt::smem_ref r;
+    SIMT_MEM int  get(uint32_t h) const { return GENERAL ? (int)simt::lds_u32(r, h * 4u) : (int)simt::lds_u16(r, h * 2u); }
+    SIMT_MEM void put(uint32_t h, int pos) const { if (GENERAL) simt::sts_u32(r, h * 4u, (uint32_t)pos); else simt::sts_u16(r, h * 2u, (uint32_t)pos); }
+};
+
+// One round = W*32 consecutive serial iterations of the find-match loop; lane l evaluates iterations l and (W == 2) 32+l.
+// Positions are a pure function of the attempt number a (>= 65): step(a) = a >> 6 (:636/:644), so the position of
+// attempt a is org + S(a) with S(a) = sum_{j<a} (j >> 6) = q * (32*(q-1) + (a & 63)), q = a >> 6 -- `org` stays the
+// same from round to round until the next match.
+//
+// The candidate of a serial iteration is the table entry -- unless an earlier iteration of this same round has the same
+// hash, in which case it is that iteration's position.  Sharing is found through the table itself while the candidate
+// words (fetched for the table entries at once) are in flight: every iteration writes its index into its bucket and
+// reads it back; one that does not find its own index ("lost") shares the bucket with the winner.  The losers write
+// once more: now the winner learns about a loser, and a loser that loses again knows the bucket has three or more
+// sharers.  Two sharers (by far the common case: a match whose source lies inside the round) are resolved exactly from
+// that -- the later iteration's candidate is the earlier one's position and its candidate word is the earlier one's
+// input word, moved by SHFL, no load; three or more take the exact path (one vote per hash bit) over the first 32
+// iterations.  At the end every bucket gets its final value: the position of the last sharer whose iteration really
+// ran (index <= f), or its old entry if none did.
+struct RoundOut { int f; bool finished; int ip, ref; };
+
+template <bool GENERAL, int W, int DUP, int LDP>
+SIMT_DEV RoundOut find_round(const EncTable<GENERAL>& T, const InWords& in, int org, uint32_t A0, bool fused,
+                             int mflimit, int lane, uint32_t lt_mask)
 {
     constexpr uint32_t FULL = 0xFFFFFFFFu;
     constexpr int HSHIFT = GENERAL ? 20 : 19;                      // :185-187 / :566-569
-    uint16_t* const T16 = (uint16_t*)sh->table;
-    uint32_t* const T32 = sh->table;
+    int pos[W]; bool valid[W]; uint32_t v[W], h[W]; int t[W]; uint32_t vmask[W];
+    InWords::Raw rp[W], rc[W];
+#pragma unroll
+    for (int s = 0; s < W; s++) {
+        const uint32_t a = A0 + 32u * s + (uint32_t)lane, q = a >> 6;
+        pos[s] = org + (int)(q * (((q - 1u) << 5) + (a & 63u)));
+        const bool special = fused && s == 0 && lane < 2;          // fused round: lane 0 = insert ip-2, lane 1 = probe+insert ip
+        if (special && lane == 0) pos[s] -= 1;                     // (the formula gives ip-1 and ip for attempts 65 and 66)
+        valid[s] = special || pos[s] + (int)q <= mflimit;          // the bounds test precedes the probe (:420 / :648)
+    }
+#pragma unroll
+    for (int s = 0; s < W; s++) rp[s] = in.raw<0>(valid[s] ? pos[s] : 0);
+#pragma unroll
+    for (int s = 0; s < W; s++) vmask[s] = simt::ballot(FULL, valid[s]);
+#pragma unroll
+    for (int s = 0; s < W; s++) { v[s] = InWords::word(rp[s]); h[s] = (v[s] * 2654435761u) >> HSHIFT; }
+#pragma unroll
+    for (int s = 0; s < W; s++) t[s] = T.get(h[s]);
+#pragma unroll
+    for (int s = 0; s < W; s++) rc[s] = in.raw<LDP>(t[s]);          // candidate words for the table entries: in flight from here
+
+    RoundOut o; o.finished = false; o.ip = o.ref = 0;
+    int partner[W];
+    uint32_t anylost = 0u, multi = 0u;
+#pragma unroll
+    for (int s = 0; s < W; s++) partner[s] = -1;
+    if (DUP == 2) {
+        simt::syncwarp(FULL);                                      // every lane has read its buckets
+#pragma unroll
+        for (int s = 0; s < W; s++) if (valid[s]) T.put(h[s], 32 * s + lane);
+        simt::syncwarp(FULL);
+        int r1[W]; bool lost[W]; bool anyl = false;
+#pragma unroll
+        for (int s = 0; s < W; s++) { r1[s] = valid[s] ? T.get(h[s]) : 32 * s + lane; lost[s] = r1[s] != 32 * s + lane; anyl = anyl || lost[s]; }
+        anylost = simt::ballot(FULL, anyl);
+        if (anylost) {
+            simt::syncwarp(FULL);
+#pragma unroll
+            for (int s = 0; s < W; s++) if (lost[s]) T.put(h[s], 32 * s + lane);
+            simt::syncwarp(FULL);
+            bool m = false;
+#pragma unroll
+            for (int s = 0; s < W; s++) {
+                const int r2 = valid[s] ? T.get(h[s]) : 32 * s + lane;
+                if (lost[s]) { partner[s] = r1[s]; m = m || r2 != 32 * s + lane; }
+                else if (r2 != 32 * s + lane) partner[s] = r2;
+            }
+            multi = simt::ballot(FULL, m);
+        }
+    }
+    if (DUP == 2 && multi == 0u) {
+        uint32_t hitm[W]; int cand[W];
+#pragma unroll
+        for (int s = 0; s < W; s++) {
+            cand[s] = t[s];
+            uint32_t pv = 0; bool lowerp = false;
+            if (anylost) {                                          // the earlier sharer's position and input word
+                const int pl = partner[s] >= 0 ? (partner[s] & 31) : lane;
+                int pp = (int)simt::shfl(FULL, (uint32_t)pos[0], pl); pv = simt::shfl(FULL, v[0], pl);
+                if (W == 2) {
+                    const int pp1 = (int)simt::shfl(FULL, (uint32_t)pos[W - 1], pl); const uint32_t pv1 = simt::shfl(FULL, v[W - 1], pl);
+                    if (partner[s] >= 32) { pp = pp1; pv = pv1; }
+                }
+                lowerp = partner[s] >= 0 && partner[s] < 32 * s + lane;
+                if (lowerp) cand[s] = pp;
+            }
+            simt::tie(rc[s].lo, anylost | multi);                   // wait for the candidate words only after the votes above
+            const uint32_t w = lowerp ? pv : InWords::word(rc[s]);
+            const bool hit = valid[s] && !(fused && s == 0 && lane == 0) &&           // (lane 0 of a fused round only inserts)
+                             (!GENERAL || cand[s] >= pos[s] - 65535) && w == v[s];    // :429 / :654, :531 / :751
+            hitm[s] = simt::ballot(FULL, hit);
+        }
+        // valid iterations are a prefix of the round (positions grow); the first event is a hit or the first invalid one
+        int nv = simt::popc(vmask[0]), fh = hitm[0] ? simt::ffs(hitm[0]) - 1 : 64;
+        if (W == 2) { nv += simt::popc(vmask[W - 1]); if (!hitm[0] && hitm[W - 1]) fh = 32 + simt::ffs(hitm[W - 1]) - 1; }
+        const int f = fh < nv ? fh : nv;                            // == 32*W: nothing happened in this round
+        // final bucket values: the last sharer whose iteration ran (index <= f) leaves its position, else the old entry
+#pragma unroll
+        for (int s = 0; s < W; s++) {
+            if (!valid[s]) continue;
+            const int me = 32 * s + lane; const bool ran = me <= f;
+            if (partner[s] < 0) T.put(h[s], ran ? pos[s] : t[s]);
+            else if (partner[s] > me) { if (!ran) T.put(h[s], t[s]); else if (partner[s] > f) T.put(h[s], pos[s]); }
+            else if (ran) T.put(h[s], pos[s]);
+        }
+        simt::syncwarp(FULL);
+        o.f = f;
+        if (f < 32 * W) {
+            if (fh >= nv) o.finished = true;                        // ran past mflimit -> last literals (:420 / :648)
+            else {
+                const bool hi = W == 2 && f >= 32;
+                o.ip = (int)simt::shfl(FULL, (uint32_t)(hi ? pos[W - 1] : pos[0]), f & 31);
+                o.ref = (int)simt::shfl(FULL, (uint32_t)(hi ? cand[W - 1] : cand[0]), f & 31);
+            }
+        }
+        return o;
+    }
+    // ---- exact path over the first 32 iterations (three or more iterations share a bucket, or DUP == 1) ----
+    if (DUP == 2) {
+        simt::syncwarp(FULL);
+#pragma unroll
+        for (int s = 0; s < W; s++) if (valid[s]) T.put(h[s], t[s]);    // (all sharers read the same old entry)
+        simt::syncwarp(FULL);
+    }
+    {
+        const uint32_t same = hash_peers<GENERAL ? 12 : 13>(h[0], valid[0], vmask[0], lane);
+        const uint32_t lower = same & lt_mask;
+        const int from = lower ? 31 - simt::clz(lower) : lane;
+        const int fwd = (int)simt::shfl(FULL, (uint32_t)pos[0], from);
+        const uint32_t fv = simt::shfl(FULL, v[0], from);
+        const int cand = lower ? fwd : t[0];
+        const uint32_t w0 = lower ? fv : InWords::word(rc[0]);
+        const bool hit = valid[0] && !(fused && lane == 0) && (!GENERAL || cand >= pos[0] - 65535) && w0 == v[0];
+        const uint32_t stop = simt::ballot(FULL, !valid[0] || hit);
+        const int f = stop ? simt::ffs(stop) - 1 : 32;
+        // commit the table writes of the serial iterations that really happened (lanes <= f), last writer per bucket
+        const uint32_t cmask = f >= 31 ? vmask[0] : (vmask[0] & ((2u << f) - 1u));
+        const uint32_t above = same & cmask & ~((2u << lane) - 1u);
+        if (((cmask >> lane) & 1u) && !above) T.put(h[0], pos[0]);
+        simt::syncwarp(FULL);
+        o.f = f < 32 ? f : -1;                                      // -1: nothing happened, and only 32 iterations were evaluated
+        if (f < 32) {
+            if (!((cmask >> f) & 1u)) o.finished = true;
+            else { o.ip = (int)simt::shfl(FULL, (uint32_t)pos[0], f); o.ref = (int)simt::shfl(FULL, (uint32_t)cand, f); }
+        }
+        return o;
+    }
+}
+
+template <bool GENERAL, int DUP, int LDP>
+SIMT_DEV int encode_block_t(EncShared* sh, const uint8_t* src, int n, uint8_t* dst, int cap, int lane, EncTune tune)
+{
+    constexpr uint32_t FULL = 0xFFFFFFFFu;
     const int mflimit = n - 12, matchlimit = n - 5;                // :361,:366 / :590,:596
-    int ip = 0, anchor = 0, op = 0, ref = 0, tok = 0;
-    uint32_t tokval = 0;
+    const uint32_t lt_mask = (1u << lane) - 1u;
     InWords in; in.init(src);
+    EncTable<GENERAL> T; T.r = simt::smem_ref_of(sh->table);
+
+    // sequence queue: lane k holds record k
+    int q = 0, op = 0;
+    int sq_anchor = 0, sq_L = 0, sq_M = 0; uint32_t sq_off = 0;
+
+    // ---- EMIT: write out the q queued sequences; false = the output does not fit (the reference returns 0) ----------
+    auto flush = [&]() -> bool {
+        const bool act = lane < q;
+        const int L = sq_L, M = sq_M;
+        const bool last = (sq_off & SEQ_LAST) != 0, nochk = (sq_off & SEQ_NOCHK) != 0;
+        const int extL = L >= 15 ? 1 + (L - 15) / 255 : 0;
+        const int extM = (!last && M >= 15) ? 1 + (M - 15) / 255 : 0;
+        const int size = act ? 1 + extL + L + (last ? 0 : 2 + extM) : 0;
+        int incl = size;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = (int)simt::shfl(FULL, (uint32_t)incl, lane >= d ? lane - d : lane);
+            if (lane >= d) incl += t;
+        }
+        const int start = op + incl - size;
+        bool bad = false;
+        if (act) {
+            if (last) bad = start + L + 1 + (L - 15 + 255) / 255 > cap;                       // :540 / :762
+            else {
+                if (!nochk) bad = start + 1 + L + (L >> 8) > cap - 8;                         // :438 / :663
+                bad = bad || start + 1 + extL + L + 2 + (M >> 8) > cap - 6                    // :501 / :728
+                          || start + size > cap;                   // (only reachable with run lengths beyond any 64 KiB block)
+            }
+        }
+        if (simt::ballot(FULL, bad)) return false;
+        int litpos = 0;
+        if (act) {
+            const int lt = L < 15 ? L : 15, mt = last ? 0 : (M < 15 ? M : 15);
+            simt::stg_u8(dst + start, (uint8_t)((lt << 4) | mt));
+            int o = start + 1;
+            if (L >= 15) { int v = L - 15; for (; v >= 255; v -= 255) simt::stg_u8(dst + o++, 255); simt::stg_u8(dst + o++, (uint8_t)v); }
+            litpos = o; o += L;
+            if (!last) {
+                simt::stg_u8(dst + o, (uint8_t)sq_off); simt::stg_u8(dst + o + 1, (uint8_t)(sq_off >> 8));       // :470 / :695
+                o += 2;
+                if (M >= 15) { int v = M - 15; for (; v >= 255; v -= 255) simt::stg_u8(dst + o++, 255); simt::stg_u8(dst + o++, (uint8_t)v); }
+            }
+        }
+        // literal runs.  All short (token-dense data): every lane copies its own run, byte by byte -- a handful of
+        // iterations for 32 sequences.  Otherwise the whole warp copies run after run, four short runs per step.
+        const int Lq = act ? L : 0;
+        const int Lmax = (int)simt::reduce_max(FULL, (uint32_t)Lq);
+        if (Lmax <= 12) {
+            const uint8_t* sp = src + sq_anchor; uint8_t* dp = dst + litpos;
+            for (int i = 0; i < Lq; i++) simt::stg_u8(dp + i, simt::ldg_nc_u8(sp + i));
+        } else
+        for (int s = 0; s < q; s += 4) {
+            int a[4], d[4], l[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                a[i] = (int)simt::shfl(FULL, (uint32_t)sq_anchor, (s + i) & 31);
+                d[i] = (int)simt::shfl(FULL, (uint32_t)litpos, (s + i) & 31);
+                l[i] = (s + i) < q ? (int)simt::shfl(FULL, (uint32_t)Lq, (s + i) & 31) : 0;
+            }
+            const int l01 = l[0] > l[1] ? l[0] : l[1], l23 = l[2] > l[3] ? l[2] : l[3];
+            if ((l01 > l23 ? l01 : l23) <= 32) {
+                uint8_t b[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) b[i] = lane < l[i] ? simt::ldg_nc_u8(src + a[i] + lane) : (uint8_t)0;
+#pragma unroll
+                for (int i = 0; i < 4; i++) if (lane < l[i]) simt::stg_u8(dst + d[i] + lane, b[i]);
+            } else {
+#pragma unroll 1
+                for (int i = s; i < s + 4 && i < q; i++) {
+                    InputSrc sp{src + (int)simt::shfl(FULL, (uint32_t)sq_anchor, i)};
+                    uint8_t* const dp = dst + (int)simt::shfl(FULL, (uint32_t)litpos, i);
+                    group_copy<32, false>(dp, sp, simt::shfl(FULL, (uint32_t)Lq, i), lane, FULL);
+                }
+            }
+        }
+        op += (int)simt::shfl(FULL, (uint32_t)incl, 31);
+        q = 0;
+        return true;
+    };
 
     for (int i = lane; i < 1024; i += 32) ((uint4*)sh->table)[i] = uint4{0, 0, 0, 0};
     simt::syncwarp(FULL);
 
+    int anchor = 0;
     if (n >= 13) {                                                 // :387 / :615 (MINLENGTH)
-        ip = 1;                                                    // :404 / :631
+        // Round state: attempt a sits at position org + S(a).  The find-match loop starts with attempt 67
+        // (findMatchAttempts = (1 << 6) + 3, :409 / :636) at position `first`: org = first - S(67) = first - 3.
+        // A fused round starts two attempts earlier: 65 and 66 are the post-match table operations on ip-2 and ip.
+        int org = 1 - 3;                                           // :404 / :631: the first probe is at position 1
+        uint32_t A0 = 67; bool fused = false, wide = false;
+        bool probe_first = false;                                  // dense matches: try the post-match probe alone first
+        int pfpos = 0;
         for (;;) {
-            // ---------------- find a match: rounds of 32 serial probe iterations (:415-429 / :642-654) ----------
-            uint32_t A = (1u << 6) + 3;                            // findMatchAttempts, :409 / :636
-            int p0 = ip;
-            bool finished = false;
-            for (;;) {
-                int pos, nxt;
-                if (A == (1u << 6) + 3) { pos = p0 + lane; nxt = pos + 1; }      // first round: 32 attempts, all with step 1
-                else {
-                    const int q = (int)(A >> 6), cross = 64 - (int)(A & 63);
-                    const int bump = lane - cross;                 // attempts before `lane` that already use step q+1
-                    pos = p0 + q * lane + (bump > 0 ? bump : 0);
-                    nxt = pos + q + (lane >= cross ? 1 : 0);
-                }
-                const bool valid = nxt <= mflimit;                 // the bounds test precedes the probe (:420 / :648)
-                uint32_t v = 0, h = 0x80000000u | (uint32_t)lane;  // invalid lanes get a key nobody shares
-                if (valid) { v = in.at(pos); h = (v * 2654435761u) >> HSHIFT; }
-                const uint32_t same = simt::match_any(FULL, h);
-                const uint32_t lower = same & ((1u << lane) - 1u);
-                const int from = lower ? 31 - simt::clz(lower) : lane;
-                const int fwd = (int)simt::shfl(FULL, (uint32_t)pos, from);
-                int cand = 0; bool hit = false;
-                if (valid) {
-                    cand = lower ? fwd : (GENERAL ? (int)T32[h] : (int)T16[h]);
-                    hit = (!GENERAL || cand >= pos - 65535) && in.at(cand) == v;        // :429 / :654
-                }
-                const uint32_t stop = simt::ballot(FULL, !valid || hit);
-                const int f = stop ? simt::ffs(stop) - 1 : 32;
-                // commit the table writes of the serial iterations that really happened, last writer per bucket
-                const bool commit = valid && lane <= f;
-                const uint32_t cmask = simt::ballot(FULL, commit);
-                const uint32_t above = same & cmask & ~((2u << lane) - 1u);
-                if (commit && !above) { if (GENERAL) T32[h] = (uint32_t)pos; else T16[h] = (uint16_t)pos; }
+            int ip = 0, ref = 0; bool again = false, have = false, finished = false;
+            if (probe_first) {
+                // The post-match table operations (:519-531 / :739-751) on their own, warp-uniform: in token-dense data
+                // the probe at ip usually hits (a zero-literal sequence) and a whole round would be wasted work.
+                const int mp = anchor, p2 = mp - 2;
+                const uint32_t v2 = in.at(p2), vi = in.at(mp);
+                constexpr int HSHIFT = GENERAL ? 20 : 19;
+                const uint32_t h2 = (v2 * 2654435761u) >> HSHIFT, h = (vi * 2654435761u) >> HSHIFT;
+                const int t = (h == h2) ? p2 : T.get(h);
+                const uint32_t w = in.at(t);
+                simt::syncwarp(FULL);                              // every lane has read the bucket
+                if (lane == 0) { T.put(h2, p2); T.put(h, mp); }
                 simt::syncwarp(FULL);
-                if (f < 32) {
-                    if (!((cmask >> f) & 1u)) { finished = true; break; }       // lane f ran past mflimit -> last literals
-                    ip = (int)simt::shfl(FULL, (uint32_t)pos, f);
-                    ref = (int)simt::shfl(FULL, (uint32_t)cand, f);
+                if ((!GENERAL || t > mp - 65536) && w == vi) { ip = mp; ref = t; again = true; have = true; }
+                else { org = mp + 1 - 3; A0 = 67; fused = false; wide = false; }
+            }
+            while (!have) {
+                if (tune.pf_dist != 0) {                            // keep the forward stream ahead of the cursor in cache
+                    const int dist = tune.pf_dist > 0 ? tune.pf_dist : -tune.pf_dist;
+                    const uint32_t qa = A0 >> 6;
+                    const int cur = org + (int)(qa * (((qa - 1u) << 5) + (A0 & 63u)));
+                    if (cur + dist > pfpos && pfpos < n) {
+                        const int p = pfpos + 128 * lane;
+                        if (lane < 4 && p < n) { if (tune.pf_dist > 0) simt::prefetch_l1(src + p); else simt::prefetch_l2(src + p); }
+                        pfpos += 512;
+                    }
+                }
+                RoundOut r;
+                int consumed;
+                if (wide && DUP == 2) { r = find_round<GENERAL, 2, DUP, LDP>(T, in, org, A0, fused, mflimit, lane, lt_mask); consumed = 64; }
+                else                  { r = find_round<GENERAL, 1, DUP, LDP>(T, in, org, A0, fused, mflimit, lane, lt_mask); consumed = 32; }
+                if (r.f < 0) { r.f = 32; consumed = 32; }           // exact path: only the first 32 iterations were evaluated
+                if (r.f >= consumed) {                              // no hit: the find-match loop goes on
+                    A0 += (uint32_t)consumed; fused = false; wide = true;
+                    continue;
+                }
+                if (r.finished) { finished = true; break; }
+                ip = r.ip; ref = r.ref; have = true;
+                again = fused && r.f == 1;                          // zero-literal sequence (:531 / :751)
+            }
+            if (finished) break;
+
+            // ---------------- catch up (:432 / :657) and count the match (:475-494 / :701-716): all loads first -------
+            int mp = ip + 4, mr = ref + 4;                          // forward cursors
+            int cnt;
+            {
+                const int a = mp + 4 * lane;
+                int room = matchlimit - a; room = room < 0 ? 0 : (room > 4 ? 4 : room);
+                const InWords::Raw ra = in.raw<0>(room > 0 ? a : 0), rr = in.raw<LDP>(room > 0 ? mr + 4 * lane : 0);
+                if (ip > anchor) {                                  // (never after a zero-literal probe hit: ip == anchor)
+                    const int k = lane + 1;
+                    const bool okb = ip - k >= anchor && ref - k >= 0;
+                    const uint8_t ba = simt::ldg_nc_u8(src + (okb ? ip - k : 0)), bb = simt::ldg_nc_u8(src + (okb ? ref - k : 0));
+                    const uint32_t ne = ~simt::ballot(FULL, okb && ba == bb);
+                    int c = ne ? simt::ffs(ne) - 1 : 32;
+                    ip -= c; ref -= c;
+                    while (c == 32) {                               // (a catch-up of 32 or more bytes: rare)
+                        const bool eq = ip - k >= anchor && ref - k >= 0 && simt::ldg_nc_u8(src + ip - k) == simt::ldg_nc_u8(src + ref - k);
+                        const uint32_t ne2 = ~simt::ballot(FULL, eq);
+                        c = ne2 ? simt::ffs(ne2) - 1 : 32;
+                        ip -= c; ref -= c;
+                    }
+                }
+                const uint32_t x = InWords::word(ra) ^ InWords::word(rr);
+                cnt = x ? (simt::ffs(x) - 1) >> 3 : 4;
+                if (cnt > room) cnt = room;
+            }
+            for (;;) {
+                const uint32_t part = simt::ballot(FULL, cnt != 4);
+                if (part) {
+                    const int pl = simt::ffs(part) - 1;
+                    mp += 4 * pl + (int)simt::shfl(FULL, (uint32_t)cnt, pl);
                     break;
                 }
-                p0 = (int)simt::shfl(FULL, (uint32_t)nxt, 31);
-                A += 32;
+                mp += 128; mr += 128;
+                const int a = mp + 4 * lane;
+                int room = matchlimit - a; room = room < 0 ? 0 : (room > 4 ? 4 : room);
+                cnt = 0;
+                if (room > 0) {
+                    const uint32_t x = in.at(a) ^ in.at(mr + 4 * lane);
+                    cnt = x ? (simt::ffs(x) - 1) >> 3 : 4;
+                    if (cnt > room) cnt = room;
+                }
             }
-            if (finished) break;
-
-            // ---------------- catch up (:432 / :657) ----------------
-            for (;;) {
-                const int k = lane + 1;
-                const bool eq = ip - k >= anchor && ref - k >= 0 &&
-                                simt::ldg_nc_u8(src + ip - k) == simt::ldg_nc_u8(src + ref - k);
-                const uint32_t ne = ~simt::ballot(FULL, eq);
-                const int cnt = ne ? simt::ffs(ne) - 1 : 32;
-                ip -= cnt; ref -= cnt;
-                if (cnt < 32) break;
+            // ---------------- park the sequence ----------------
+            const int L = ip - anchor;
+            if (lane == q) {
+                sq_anchor = anchor; sq_L = L; sq_M = mp - (ip + 4);
+                sq_off = (uint32_t)(ip - ref) | (again ? SEQ_NOCHK : 0u);
             }
-
-            // ---------------- literal run (:435-466 / :660-691) ----------------
-            {
-                const int L = ip - anchor;
-                tok = op++;
-                if (op + L + (L >> 8) > cap - 8) return 0;         // :438 / :663
-                if (L >= 15) { tokval = 0xF0; op += put_len_ext(dst, op, cap, L - 15, lane); }
-                else tokval = (uint32_t)L << 4;
-                InputSrc s{src + anchor};
-                group_copy<32, false>(dst + op, s, (uint32_t)L, lane, FULL);
-                op += L;
-            }
-
-            // ---------------- match(es) ----------------
-            bool again;
-            do {
-                if (lane == 0 && (!GENERAL || op + 2 <= cap)) {    // :470 / :695
-                    simt::stg_u8(dst + op, (uint8_t)(ip - ref)); simt::stg_u8(dst + op + 1, (uint8_t)((ip - ref) >> 8));
-                }
-                op += 2;
-                ip += 4; ref += 4; anchor = ip;
-                for (;;) {                                         // count equal bytes up to matchlimit (:475-494 / :701-716)
-                    const int a = ip + 4 * lane;
-                    int room = matchlimit - a; room = room < 0 ? 0 : (room > 4 ? 4 : room);
-                    int cnt = 0;
-                    if (room > 0) {
-                        const uint32_t x = in.at(a) ^ in.at(ref + 4 * lane);
-                        cnt = x ? (simt::ffs(x) - 1) >> 3 : 4;
-                        if (cnt > room) cnt = room;
-                    }
-                    const uint32_t part = simt::ballot(FULL, cnt != 4);
-                    if (part) {
-                        const int fl = simt::ffs(part) - 1;
-                        ip += 4 * fl + (int)simt::shfl(FULL, (uint32_t)cnt, fl);
-                        break;
-                    }
-                    ip += 128; ref += 128;
-                }
-                const int M = ip - anchor;
-                if (op + (M >> 8) > cap - 6) return 0;             // :501 / :728
-                if (M >= 15) { tokval |= 15; op += put_len_ext(dst, op, cap, M - 15, lane); }
-                else tokval |= (uint32_t)M;
-                if (lane == 0) simt::stg_u8(dst + tok, (uint8_t)tokval);
-
-                again = false;
-                if (ip > mflimit) { anchor = ip; finished = true; break; }      // :516 / :736
-                // table fix-up for ip-2, then probe ip itself (:519-531 / :739-751); reads first, then lane 0 writes
-                const int p2 = ip - 2;
-                const uint32_t h2 = (in.at(p2) * 2654435761u) >> HSHIFT;
-                const uint32_t vi = in.at(ip);
-                const uint32_t h = (vi * 2654435761u) >> HSHIFT;
-                ref = (h == h2) ? p2 : (GENERAL ? (int)T32[h] : (int)T16[h]);
-                simt::syncwarp(FULL);
-                if (lane == 0) {
-                    if (GENERAL) { T32[h2] = (uint32_t)p2; T32[h] = (uint32_t)ip; }
-                    else         { T16[h2] = (uint16_t)p2; T16[h] = (uint16_t)ip; }
-                }
-                simt::syncwarp(FULL);
-                if ((!GENERAL || ref > ip - 65536) && in.at(ref) == vi) {
-                    tok = op++; tokval = 0; again = true;          // zero-literal sequence (:531 / :751)
-                }
-            } while (again);
-            if (finished) break;
-            anchor = ip++;                                         // :534 / :754
+            if (++q == 32 && !flush()) return 0;
+            anchor = mp;
+            if (mp > mflimit) break;                                // :516 / :736
+            // What follows a match (:519-534 / :739-755): insert ip-2, probe + insert ip, then the find-match loop from
+            // ip+1.  Short literal runs predict another immediate hit: do the probe alone first.  Otherwise all of it
+            // is one fused round: attempts 65, 66 = ip-2, ip; 67.. = the loop.  S(66) = 2, so org = mp - 2.
+            probe_first = L < 8;
+            org = mp - 2; A0 = 65; fused = true;
+            wide = L >= 24;                                         // long literal runs: the next match is probably > 30 bytes away
         }
     }
 
     // ---------------- last literals (:540-551 / :760-767) ----------------
-    {
-        const int R = n - anchor;
-        if (op + R + 1 + (R - 15 + 255) / 255 > cap) return 0;
-        tok = op++;
-        if (R >= 15) { if (lane == 0) simt::stg_u8(dst + tok, 0xF0); op += put_len_ext(dst, op, cap, R - 15, lane); }
-        else if (lane == 0) simt::stg_u8(dst + tok, (uint8_t)(R << 4));
-        InputSrc s{src + anchor};
-        group_copy<32, false>(dst + op, s, (uint32_t)R, lane, FULL);
-        op += R;
-    }
+    if (lane == q) { sq_anchor = anchor; sq_L = n - anchor; sq_off = SEQ_LAST; sq_M = 0; }
+    ++q;
+    if (!flush()) return 0;
     return op;
 }
 
 // LZ4_compress_limitedOutput dispatch (original/lz4.c:774-792)
-SIMT_DEV int encode_block(EncShared* sh, const uint8_t* src, int n, uint8_t* dst, int cap, int lane)
+template <int DUP = 2, int LDP = 0>
+SIMT_DEV int encode_block(EncShared* sh, const uint8_t* src, int n, uint8_t* dst, int cap, int lane, EncTune tune = EncTune{0})
 {
     if (n < 0 || cap < 0) return 0;
     simt::syncwarp(0xFFFFFFFFu);                                   // previous block's table users are done
-    return n < LZ4_64KLIMIT ? encode_block_t<false>(sh, src, n, dst, cap, lane)
-                            : encode_block_t<true>(sh, src, n, dst, cap, lane);
+    return n < LZ4_64KLIMIT ? encode_block_t<false, DUP, LDP>(sh, src, n, dst, cap, lane, tune)
+                            : encode_block_t<true, DUP, LDP>(sh, src, n, dst, cap, lane, tune);
 }
 
 }  // namespace lz4b200

@@ -20,6 +20,7 @@ namespace simt {
 SIMT_DEV uint32_t shfl(uint32_t mask, uint32_t v, int src) { return __shfl_sync(mask, v, src); }
 SIMT_DEV uint32_t ballot(uint32_t mask, bool p) { return __ballot_sync(mask, p); }
 SIMT_DEV uint32_t match_any(uint32_t mask, uint32_t v) { return __match_any_sync(mask, v); }
+SIMT_DEV uint32_t reduce_max(uint32_t mask, uint32_t v) { return __reduce_max_sync(mask, v); }     // REDUX
 SIMT_DEV void syncwarp(uint32_t mask) { __syncwarp(mask); }
 SIMT_DEV int ffs(uint32_t v) { return __ffs((int)v); }
 SIMT_DEV int clz(uint32_t v) { return __clz((int)v); }
@@ -44,6 +45,25 @@ SIMT_DEV uint4    ldg_nc_v4(const void* p) { return __ldg((const uint4*)p); }
 SIMT_DEV void stg_u8(uint8_t* p, uint8_t v) { *p = v; }
 SIMT_DEV void stg_u32(void* p, uint32_t v) { *(uint32_t*)p = v; }
 SIMT_DEV void stg_v4(void* p, uint4 v) { *(uint4*)p = v; }
+// cached in L2 only (random probes that would evict the streaming window from L1).  Measured on B200: the
+// L1::no_allocate form of the read-only load also loses the line in L2 (30x DRAM read amplification) -- not used.
+SIMT_DEV uint32_t ldg_cg_u32(const void* p) { uint32_t v; asm("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+// Scheduling fence without an instruction: `x` formally depends on `dep`, so the first use of x (the point where the
+// warp waits for the load that produces it) cannot be scheduled before dep has been computed.
+SIMT_DEV void tie(uint32_t& x, uint32_t dep) { asm volatile("" : "+r"(x) : "r"(dep)); }
+
+// A block of shared memory addressed by its 32-bit shared-window address (one register, computed once; LDS/STS take
+// it with an immediate-free register offset -- no generic-pointer conversion in the loop).
+struct smem_ref { uint32_t a; };
+SIMT_DEV smem_ref smem_ref_of(const void* p) { smem_ref r; r.a = (uint32_t)__cvta_generic_to_shared(p); asm volatile("" : "+r"(r.a)); return r; }
+SIMT_DEV uint32_t lds_u16(smem_ref r, uint32_t off) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(r.a + off) : "memory"); return v; }
+SIMT_DEV uint32_t lds_u32(smem_ref r, uint32_t off) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(r.a + off) : "memory"); return v; }
+SIMT_DEV void sts_u16(smem_ref r, uint32_t off, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" :: "r"(r.a + off), "h"((uint16_t)v) : "memory"); }
+SIMT_DEV void sts_u32(smem_ref r, uint32_t off, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(r.a + off), "r"(v) : "memory"); }
+
+// software prefetch of the line holding *p (no destination register, never faults the warp's progress)
+SIMT_DEV void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
+SIMT_DEV void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 
 // ---- mbarrier + 1-D bulk async copy (global -> shared::cta), the TMA engine's non-tensor form --------------
 struct mbar_t { uint64_t v; };

@@ -55,6 +55,8 @@ void dec_entry(int lane, void* arg)
     }
 }
 
+int g_enc_variant = 2;
+
 struct EncJob {
     int nblocks; const uint8_t* const* src; const int* n; uint8_t* const* dst; const int* cap; int* result;
     EncShared* sh;
@@ -64,7 +66,8 @@ void enc_entry(int lane, void* arg)
 {
     EncJob* j = (EncJob*)arg;
     for (int b = 0; b < j->nblocks; b++) {
-        int r = encode_block(j->sh, j->src[b], j->n[b], j->dst[b], j->cap[b], lane);
+        int r = g_enc_variant == 1 ? encode_block<1>(j->sh, j->src[b], j->n[b], j->dst[b], j->cap[b], lane)
+                                   : encode_block<2>(j->sh, j->src[b], j->n[b], j->dst[b], j->cap[b], lane);
         if (lane == 0) j->result[b] = r;
     }
 }
@@ -92,6 +95,8 @@ int emu_encode_hc(const uint8_t* src, int n, uint8_t* dst, int cap)
     free(st);
     return r;
 }
+
+void emu_set_encode_variant(int v) { g_enc_variant = v; }
 
 void emu_encode(int nblocks, const uint8_t* const* src, const int* n, uint8_t* const* dst, const int* cap,
                 int* result, uint64_t sched_seed)

@@ -33,6 +33,7 @@ static void finish(Slot& s)
         case OP_SYNC: s.res[l] = 0; break;
         case OP_BALLOT: { uint32_t r = 0; for (int k = 0; k < NL; k++) if ((s.mask >> k & 1) && s.a[k]) r |= 1u << k; s.res[l] = r; } break;
         case OP_SHFL: { int src = (int)(s.b[l] & 31); s.res[l] = (s.mask >> src & 1) ? s.a[src] : s.a[l]; } break;
+        case OP_RMAX: { uint32_t r = 0; for (int k = 0; k < NL; k++) if ((s.mask >> k & 1) && s.a[k] > r) r = s.a[k]; s.res[l] = r; } break;
         case OP_MATCH: { uint32_t r = 0; for (int k = 0; k < NL; k++) if ((s.mask >> k & 1) && s.a[k] == s.a[l]) r |= 1u << k; s.res[l] = r; } break;
         }
     }

@@ -21,13 +21,14 @@ void run_warp(void (*fn)(int lane, void* arg), void* arg, uint64_t sched_seed);
 uint32_t collective(int op, uint32_t mask, uint32_t a, uint32_t b);
 int current_lane();
 void yield();          // let the other lanes run (used by emulated spin-waits)
-enum { OP_SYNC = 0, OP_BALLOT = 1, OP_SHFL = 2, OP_MATCH = 3 };
+enum { OP_SYNC = 0, OP_BALLOT = 1, OP_SHFL = 2, OP_MATCH = 3, OP_RMAX = 4 };
 }
 
 namespace simt {
 static inline uint32_t shfl(uint32_t mask, uint32_t v, int src) { return simt_emu::collective(simt_emu::OP_SHFL, mask, v, (uint32_t)src); }
 static inline uint32_t ballot(uint32_t mask, bool p) { return simt_emu::collective(simt_emu::OP_BALLOT, mask, p ? 1u : 0u, 0); }
 static inline uint32_t match_any(uint32_t mask, uint32_t v) { return simt_emu::collective(simt_emu::OP_MATCH, mask, v, 0); }
+static inline uint32_t reduce_max(uint32_t mask, uint32_t v) { return simt_emu::collective(simt_emu::OP_RMAX, mask, v, 0); }
 static inline void syncwarp(uint32_t mask) { simt_emu::collective(simt_emu::OP_SYNC, mask, 0, 0); }
 static inline int ffs(uint32_t v) { return __builtin_ffs((int)v); }
 static inline int clz(uint32_t v) { return v ? __builtin_clz(v) : 32; }
@@ -45,6 +46,16 @@ static inline uint4    ldg_nc_v4(const void* p) { return ldg_v4(p); }
 static inline void stg_u8(uint8_t* p, uint8_t v) { *p = v; }
 static inline void stg_u32(void* p, uint32_t v) { memcpy(p, &v, 4); }
 static inline void stg_v4(void* p, uint4 v) { memcpy(p, &v, 16); }
+static inline uint32_t ldg_cg_u32(const void* p) { return ldg_u32(p); }
+static inline void tie(uint32_t&, uint32_t) {}
+struct smem_ref { uint8_t* p; };
+static inline smem_ref smem_ref_of(const void* p) { return smem_ref{(uint8_t*)p}; }
+static inline uint32_t lds_u16(smem_ref r, uint32_t off) { uint16_t v; memcpy(&v, r.p + off, 2); return v; }
+static inline uint32_t lds_u32(smem_ref r, uint32_t off) { uint32_t v; memcpy(&v, r.p + off, 4); return v; }
+static inline void sts_u16(smem_ref r, uint32_t off, uint32_t v) { uint16_t t = (uint16_t)v; memcpy(r.p + off, &t, 2); }
+static inline void sts_u32(smem_ref r, uint32_t off, uint32_t v) { memcpy(r.p + off, &v, 4); }
+static inline void prefetch_l1(const void*) {}
+static inline void prefetch_l2(const void*) {}
 
 // async bulk copy global -> shared with an mbarrier: immediate in the emulator
 struct mbar_t { uint64_t v; };

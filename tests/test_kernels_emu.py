@@ -67,6 +67,13 @@ def test_encode_unaligned_buffers(skew):
         assert (r, o) == oracle.encode(b)
 
 
+@pytest.mark.parametrize("variant", [1])
+def test_encode_other_duplicate_detectors(variant):
+    """The always-exact (vote-per-hash-bit, 32 iterations per round) form of the round gives the same bytes as the default."""
+    blocks = [cases.content(m, n, seed=90 + i).tobytes() for i, m in enumerate(cases.MODELS) for n in (65536, 4097)]
+    _enc_check(blocks, sched_seed=6, variant=variant)
+
+
 def test_encode_schedule_independent():
     """Lanes are scheduled in different orders: the result may not depend on lock-step luck."""
     blocks = [cases.content("lowent", 20000, seed=1).tobytes(), cases.content("mixed", 20000, seed=2).tobytes()]
