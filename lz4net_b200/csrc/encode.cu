@@ -5,17 +5,19 @@
 
 namespace lz4b200 {
 
-// ---- fast encoder: one warp (= one CTA) per block, persistent, dynamic block hand-out --------------------------------
-// The position table is dynamic shared memory so the launcher can also use its size to pin the number of CTAs per SM.
-// (min 16 CTAs per SM only tells ptxas how many registers it may use: 128.  With the bare bound it assumes the
-// hardware maximum of 32 CTAs, caps the kernel at 64 registers and spills; shared memory allows 13 CTAs anyway.)
+// ---- fast encoder: one warp per block, persistent, dynamic block hand-out --------------------------------------------
+// All encoder warps of an SM live in ONE CTA (up to 14 warps x 16 KiB of position tables = 224 KiB of dynamic shared
+// memory): separate CTAs would each pay 1 KiB of system-reserved shared memory, which costs the 14th warp.  The warps
+// never synchronise with each other.  (The launch bound only tells ptxas how many registers it may use: 65536 / 448.)
+constexpr int ENC_MAX_WARPS = 14;
+
 template <int DUP, int LDP>
-__global__ void __launch_bounds__(32, 16)
+__global__ void __launch_bounds__(32 * ENC_MAX_WARPS, 1)
 lz4_encode_fast_kernel(BatchArgs a, uint32_t* counter, EncTune tune)
 {
     extern __shared__ __align__(16) uint8_t smem[];
-    EncShared* sh = (EncShared*)smem;
-    const int lane = threadIdx.x;
+    EncShared* sh = (EncShared*)smem + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     for (;;) {
         uint32_t b = 0;
         if (lane == 0) b = atomicAdd(counter, 1u);
@@ -27,37 +29,39 @@ lz4_encode_fast_kernel(BatchArgs a, uint32_t* counter, EncTune tune)
 }
 
 template <int DUP, int LDP>
-static cudaError_t launch_fast_t(const BatchArgs& a, uint32_t* counter, int dyn, long long grid, int prefetch, cudaStream_t stream)
+static cudaError_t launch_fast_t(const BatchArgs& a, uint32_t* counter, int dyn, long long grid, int warps, int prefetch, cudaStream_t stream)
 {
     cudaError_t e = cudaFuncSetAttribute(lz4_encode_fast_kernel<DUP, LDP>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
     if (e != cudaSuccess) return e;
-    lz4_encode_fast_kernel<DUP, LDP><<<(unsigned)grid, 32, dyn, stream>>>(a, counter, EncTune{prefetch});
+    lz4_encode_fast_kernel<DUP, LDP><<<(unsigned)grid, 32 * warps, dyn, stream>>>(a, counter, EncTune{prefetch});
     return cudaGetLastError();
 }
 
-cudaError_t launch_encode_fast(const BatchArgs& a, uint32_t* counter, int ctas_per_sm, int prefetch, int variant,
+cudaError_t launch_encode_fast(const BatchArgs& a, uint32_t* counter, int warps_per_sm, int prefetch, int variant,
                                const DeviceInfo& dev, cudaStream_t stream, int64_t* launches)
 {
     if (a.n_blocks <= 0) return cudaSuccess;
-    // each CTA costs its dynamic bytes + 1 KiB of system-reserved shared memory
-    const int max_ctas = dev.smem_per_sm / ((int)sizeof(EncShared) + 1024);
-    if (ctas_per_sm < 1 || ctas_per_sm > max_ctas) ctas_per_sm = max_ctas;
-    if (ctas_per_sm > 32) ctas_per_sm = 32;
-    int dyn = dev.smem_per_sm / ctas_per_sm - 1024;
-    dyn &= ~1023;
-    if (dyn > dev.smem_optin) dyn = dev.smem_optin & ~1023;
-    if (dyn < (int)sizeof(EncShared)) dyn = (int)sizeof(EncShared);
+    int max_warps = dev.smem_optin / (int)sizeof(EncShared);
+    if (max_warps > ENC_MAX_WARPS) max_warps = ENC_MAX_WARPS;
+    if (max_warps < 1) max_warps = 1;
+    if (warps_per_sm < 1 || warps_per_sm > max_warps) warps_per_sm = max_warps;
+    // small batches: spread the blocks over the SMs first
+    long long grid = dev.num_sms;
+    int warps = warps_per_sm;
+    if (a.n_blocks < (long long)dev.num_sms * warps) {
+        warps = (int)((a.n_blocks + dev.num_sms - 1) / dev.num_sms);
+        grid = (a.n_blocks + warps - 1) / warps;
+    }
+    const int dyn = warps * (int)sizeof(EncShared);
     cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), stream);
     if (e != cudaSuccess) return e;
-    long long grid = (long long)dev.num_sms * ctas_per_sm;
-    if (grid > a.n_blocks) grid = a.n_blocks;
     if (launches) ++*launches;
     switch (variant) {                      // variant % 10: how same-hash iterations of one round are found (lz4_encode.cuh);
                                             // variant / 10: candidate loads through L1 (0) or L2 only (1)
-    case 1:  return launch_fast_t<1, 0>(a, counter, dyn, grid, prefetch, stream);  // always exact: one vote per hash bit
-    case 11: return launch_fast_t<1, 1>(a, counter, dyn, grid, prefetch, stream);
-    case 12: return launch_fast_t<2, 1>(a, counter, dyn, grid, prefetch, stream);
-    default: return launch_fast_t<2, 0>(a, counter, dyn, grid, prefetch, stream);  // through the table, pairs resolved in place
+    case 1:  return launch_fast_t<1, 0>(a, counter, dyn, grid, warps, prefetch, stream);  // always exact: one vote per hash bit
+    case 11: return launch_fast_t<1, 1>(a, counter, dyn, grid, warps, prefetch, stream);
+    case 12: return launch_fast_t<2, 1>(a, counter, dyn, grid, warps, prefetch, stream);
+    default: return launch_fast_t<2, 0>(a, counter, dyn, grid, warps, prefetch, stream);  // through the table, pairs resolved in place
     }
 }
 

@@ -85,7 +85,9 @@ struct EncTable {
 // ran (index <= f), or its old entry if none did.
 struct RoundOut { int f; bool finished; int ip, ref; };
 
-template <bool GENERAL, int W, int DUP, int LDP>
+// SIMPLE: every attempt of the round still has step 1 and lies inside the block (known from two warp-uniform tests):
+// positions are consecutive and every iteration is valid.
+template <bool GENERAL, int W, int DUP, int LDP, bool SIMPLE>
 SIMT_DEV RoundOut find_round(const EncTable<GENERAL>& T, const InWords& in, int org, uint32_t A0, bool fused,
                              int mflimit, int lane, uint32_t lt_mask)
 {
@@ -93,18 +95,22 @@ SIMT_DEV RoundOut find_round(const EncTable<GENERAL>& T, const InWords& in, int 
     constexpr int HSHIFT = GENERAL ? 20 : 19;                      // :185-187 / :566-569
     int pos[W]; bool valid[W]; uint32_t v[W], h[W]; int t[W]; uint32_t vmask[W];
     InWords::Raw rp[W], rc[W];
+    const int p0 = org + (int)A0 - 64;                             // SIMPLE: attempt A0 + i sits at p0 + i (S(a) = a - 64 up to a = 128)
 #pragma unroll
     for (int s = 0; s < W; s++) {
-        const uint32_t a = A0 + 32u * s + (uint32_t)lane, q = a >> 6;
-        pos[s] = org + (int)(q * (((q - 1u) << 5) + (a & 63u)));
         const bool special = fused && s == 0 && lane < 2;          // fused round: lane 0 = insert ip-2, lane 1 = probe+insert ip
+        if (SIMPLE) { pos[s] = p0 + 32 * s + lane; valid[s] = true; }
+        else {
+            const uint32_t a = A0 + 32u * s + (uint32_t)lane, q = a >> 6;
+            pos[s] = org + (int)(q * (((q - 1u) << 5) + (a & 63u)));
+            valid[s] = special || pos[s] + (int)q <= mflimit;      // the bounds test precedes the probe (:420 / :648)
+        }
         if (special && lane == 0) pos[s] -= 1;                     // (the formula gives ip-1 and ip for attempts 65 and 66)
-        valid[s] = special || pos[s] + (int)q <= mflimit;          // the bounds test precedes the probe (:420 / :648)
     }
 #pragma unroll
     for (int s = 0; s < W; s++) rp[s] = in.raw<0>(valid[s] ? pos[s] : 0);
 #pragma unroll
-    for (int s = 0; s < W; s++) vmask[s] = simt::ballot(FULL, valid[s]);
+    for (int s = 0; s < W; s++) vmask[s] = SIMPLE ? FULL : simt::ballot(FULL, valid[s]);
 #pragma unroll
     for (int s = 0; s < W; s++) { v[s] = InWords::word(rp[s]); h[s] = (v[s] * 2654435761u) >> HSHIFT; }
 #pragma unroll
@@ -149,10 +155,13 @@ SIMT_DEV RoundOut find_round(const EncTable<GENERAL>& T, const InWords& in, int 
             uint32_t pv = 0; bool lowerp = false;
             if (anylost) {                                          // the earlier sharer's position and input word
                 const int pl = partner[s] >= 0 ? (partner[s] & 31) : lane;
-                int pp = (int)simt::shfl(FULL, (uint32_t)pos[0], pl); pv = simt::shfl(FULL, v[0], pl);
+                int pp; pv = simt::shfl(FULL, v[0], pl);
+                if (SIMPLE) pp = p0 + partner[s] - ((fused && partner[s] == 0) ? 1 : 0);     // a position follows from its index
+                else pp = (int)simt::shfl(FULL, (uint32_t)pos[0], pl);
                 if (W == 2) {
-                    const int pp1 = (int)simt::shfl(FULL, (uint32_t)pos[W - 1], pl); const uint32_t pv1 = simt::shfl(FULL, v[W - 1], pl);
-                    if (partner[s] >= 32) { pp = pp1; pv = pv1; }
+                    const uint32_t pv1 = simt::shfl(FULL, v[W - 1], pl);
+                    if (!SIMPLE) { const int pp1 = (int)simt::shfl(FULL, (uint32_t)pos[W - 1], pl); if (partner[s] >= 32) pp = pp1; }
+                    if (partner[s] >= 32) pv = pv1;
                 }
                 lowerp = partner[s] >= 0 && partner[s] < 32 * s + lane;
                 if (lowerp) cand[s] = pp;
@@ -182,7 +191,7 @@ SIMT_DEV RoundOut find_round(const EncTable<GENERAL>& T, const InWords& in, int 
             if (fh >= nv) o.finished = true;                        // ran past mflimit -> last literals (:420 / :648)
             else {
                 const bool hi = W == 2 && f >= 32;
-                o.ip = (int)simt::shfl(FULL, (uint32_t)(hi ? pos[W - 1] : pos[0]), f & 31);
+                o.ip = SIMPLE ? p0 + f : (int)simt::shfl(FULL, (uint32_t)(hi ? pos[W - 1] : pos[0]), f & 31);   // (f == 0 never hits in a fused round)
                 o.ref = (int)simt::shfl(FULL, (uint32_t)(hi ? cand[W - 1] : cand[0]), f & 31);
             }
         }
@@ -350,8 +359,14 @@ SIMT_DEV int encode_block_t(EncShared* sh, const uint8_t* src, int n, uint8_t* d
                 }
                 RoundOut r;
                 int consumed;
-                if (wide && DUP == 2) { r = find_round<GENERAL, 2, DUP, LDP>(T, in, org, A0, fused, mflimit, lane, lt_mask); consumed = 64; }
-                else                  { r = find_round<GENERAL, 1, DUP, LDP>(T, in, org, A0, fused, mflimit, lane, lt_mask); consumed = 32; }
+                const bool w2 = wide && DUP == 2;
+                consumed = w2 ? 64 : 32;
+                // step 1 up to attempt 128 (and 2 for attempt 128 itself), everything inside the block?
+                const bool simple = A0 + (uint32_t)consumed - 1u <= 128u && org + (int)A0 - 64 + consumed + 1 <= mflimit;
+                if (w2) r = simple ? find_round<GENERAL, 2, DUP, LDP, true>(T, in, org, A0, fused, mflimit, lane, lt_mask)
+                                   : find_round<GENERAL, 2, DUP, LDP, false>(T, in, org, A0, fused, mflimit, lane, lt_mask);
+                else    r = simple ? find_round<GENERAL, 1, DUP, LDP, true>(T, in, org, A0, fused, mflimit, lane, lt_mask)
+                                   : find_round<GENERAL, 1, DUP, LDP, false>(T, in, org, A0, fused, mflimit, lane, lt_mask);
                 if (r.f < 0) { r.f = 32; consumed = 32; }           // exact path: only the first 32 iterations were evaluated
                 if (r.f >= consumed) {                              // no hit: the find-match loop goes on
                     A0 += (uint32_t)consumed; fused = false; wide = true;
