@@ -489,7 +489,7 @@ int lz4b200_set_option(lz4b200_ctx* c, const char* key, int64_t value)
     std::string k(key);
     if (k == "decode_lanes") {
         const int64_t g = value % 100;                 // 100 + G = the output-staged variant of the G-lane decoder
-        if ((g != 8 && g != 16 && g != 32) || (value != g && value != 100 + g)) return fail(LZ4B200_E_ARG, "decode_lanes must be 8, 16, 32 (or 100 + that)");
+        if ((g != 4 && g != 8 && g != 16 && g != 32) || (value != g && value != 100 + g)) return fail(LZ4B200_E_ARG, "decode_lanes must be 4, 8, 16, 32 (or 100 + that)");
         c->decode_lanes = (int)value; c->decode_lanes_auto = false;
     }
     else if (k == "decode_lanes_auto") { c->decode_lanes_auto = value != 0; }

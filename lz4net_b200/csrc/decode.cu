@@ -76,6 +76,7 @@ cudaError_t launch_decode(const BatchArgs& a, bool known_len, int lanes, uint32_
     if (launches) ++*launches;
     const bool staged = lanes >= 100;            // lanes = 100 + G selects the output-staged variant
     switch (lanes % 100) {
+    case 4:  return launch_g<4>(a, known_len, staged, counter, dev, stream);
     case 8:  return launch_g<8>(a, known_len, staged, counter, dev, stream);
     case 16: return launch_g<16>(a, known_len, staged, counter, dev, stream);
     default: return launch_g<32>(a, known_len, staged, counter, dev, stream);

@@ -32,7 +32,7 @@ constexpr int DEC_MIRROR = 64;                                  // bytes of the 
 constexpr int DEC_AHEAD = 64;                                   // the fast path may read this far past the cursor
 
 template <int G> struct DecGeom {
-    static constexpr int LOG_CHUNK = G == 32 ? 10 : (G == 16 ? 9 : 8);     // 1 KiB / 512 B / 256 B bulk copies
+    static constexpr int LOG_CHUNK = G == 32 ? 10 : (G == 16 ? 9 : (G == 8 ? 8 : 7));     // 1 KiB / 512 / 256 / 128 B bulk copies
     static constexpr int CHUNK = 1 << LOG_CHUNK;
     static constexpr int RING = CHUNK * DEC_SLOTS;
 };
@@ -303,7 +303,7 @@ SIMT_DEV int decode_block(DecStream<G>& st, const uint8_t* src, int isize, uint8
 // careful-path sequence ends with a group synchronisation).
 // ---------------------------------------------------------------------------------------------------------------------
 template <int G> struct DecStageGeom {
-    static constexpr int FLUSH_AT = G == 8 ? 256 : 512;            // flush once this many bytes are staged.  (A flush by one group stalls the
+    static constexpr int FLUSH_AT = G <= 8 ? 256 : 512;           // flush once this many bytes are staged.  (A flush by one group stalls the
                                                                    // other groups of its warp; 1 KiB for G = 8 was measured slower: it costs a third of the resident warps.)
     static constexpr int SIZE = FLUSH_AT + 32 + 64 + 16;           // + one more fast sequence + slack
 };

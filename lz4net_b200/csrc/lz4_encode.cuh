@@ -176,14 +176,14 @@ SIMT_DEV RoundOut find_round(const EncTable<GENERAL>& T, const InWords& in, int 
         int nv = simt::popc(vmask[0]), fh = hitm[0] ? simt::ffs(hitm[0]) - 1 : 64;
         if (W == 2) { nv += simt::popc(vmask[W - 1]); if (!hitm[0] && hitm[W - 1]) fh = 32 + simt::ffs(hitm[W - 1]) - 1; }
         const int f = fh < nv ? fh : nv;                            // == 32*W: nothing happened in this round
-        // final bucket values: the last sharer whose iteration ran (index <= f) leaves its position, else the old entry
+        // final bucket values: the last sharer whose iteration ran (index <= f) leaves its position, else the old entry.
+        // Without a partner I write either way; of two sharers the later one writes if it ran, the earlier one if the
+        // later one did not (its own position if it ran itself, else the old entry).
 #pragma unroll
         for (int s = 0; s < W; s++) {
-            if (!valid[s]) continue;
             const int me = 32 * s + lane; const bool ran = me <= f;
-            if (partner[s] < 0) T.put(h[s], ran ? pos[s] : t[s]);
-            else if (partner[s] > me) { if (!ran) T.put(h[s], t[s]); else if (partner[s] > f) T.put(h[s], pos[s]); }
-            else if (ran) T.put(h[s], pos[s]);
+            const bool wr = valid[s] && (partner[s] < 0 || (partner[s] > me ? (!ran || partner[s] > f) : ran));
+            if (wr) T.put(h[s], ran ? pos[s] : t[s]);
         }
         simt::syncwarp(FULL);
         o.f = f;
@@ -347,16 +347,6 @@ SIMT_DEV int encode_block_t(EncShared* sh, const uint8_t* src, int n, uint8_t* d
                 else { org = mp + 1 - 3; A0 = 67; fused = false; wide = false; }
             }
             while (!have) {
-                if (tune.pf_dist != 0) {                            // keep the forward stream ahead of the cursor in cache
-                    const int dist = tune.pf_dist > 0 ? tune.pf_dist : -tune.pf_dist;
-                    const uint32_t qa = A0 >> 6;
-                    const int cur = org + (int)(qa * (((qa - 1u) << 5) + (A0 & 63u)));
-                    if (cur + dist > pfpos && pfpos < n) {
-                        const int p = pfpos + 128 * lane;
-                        if (lane < 4 && p < n) { if (tune.pf_dist > 0) simt::prefetch_l1(src + p); else simt::prefetch_l2(src + p); }
-                        pfpos += 512;
-                    }
-                }
                 RoundOut r;
                 int consumed;
                 const bool w2 = wide && DUP == 2;
@@ -429,6 +419,11 @@ SIMT_DEV int encode_block_t(EncShared* sh, const uint8_t* src, int n, uint8_t* d
             if (++q == 32 && !flush()) return 0;
             anchor = mp;
             if (mp > mflimit) break;                                // :516 / :736
+            if (tune.pf_dist != 0 && mp + (tune.pf_dist > 0 ? tune.pf_dist : -tune.pf_dist) > pfpos && pfpos < n) {
+                const int p = pfpos + 128 * lane;                   // keep the forward stream ahead of the cursor in cache
+                if (lane < 4 && p < n) { if (tune.pf_dist > 0) simt::prefetch_l1(src + p); else simt::prefetch_l2(src + p); }
+                pfpos += 512;
+            }
             // What follows a match (:519-534 / :739-755): insert ip-2, probe + insert ip, then the find-match loop from
             // ip+1.  Short literal runs predict another immediate hit: do the probe alone first.  Otherwise all of it
             // is one fused round: attempts 65, 66 = ip-2, ip; 67.. = the loop.  S(66) = 2, so org = mp - 2.

@@ -16,17 +16,19 @@ struct DecJob {
     int G; bool known; int nblocks;
     const uint8_t* const* src; const int* isize; uint8_t* const* dst; const int* cap; int* result;
     bool staged;
-    DecRing<32> r32[1]; DecRing<16> r16[2]; DecRing<8> r8[4];
-    DecStage<32> s32[1]; DecStage<16> s16[2]; DecStage<8> s8[4];
+    DecRing<32> r32[1]; DecRing<16> r16[2]; DecRing<8> r8[4]; DecRing<4> r4[8];
+    DecStage<32> s32[1]; DecStage<16> s16[2]; DecStage<8> s8[4]; DecStage<4> s4[8];
     template <int G> DecStage<G>* stages();
     template <int G> DecRing<G>* rings();
 };
 template <> DecRing<32>* DecJob::rings<32>() { return r32; }
 template <> DecRing<16>* DecJob::rings<16>() { return r16; }
 template <> DecRing<8>*  DecJob::rings<8>()  { return r8; }
+template <> DecRing<4>*  DecJob::rings<4>()  { return r4; }
 template <> DecStage<32>* DecJob::stages<32>() { return s32; }
 template <> DecStage<16>* DecJob::stages<16>() { return s16; }
 template <> DecStage<8>*  DecJob::stages<8>()  { return s8; }
+template <> DecStage<4>*  DecJob::stages<4>()  { return s4; }
 
 template <int G, bool KNOWN>
 void dec_lane(int wl, DecJob* j)
@@ -49,6 +51,7 @@ void dec_entry(int lane, void* arg)
 {
     DecJob* j = (DecJob*)arg;
     switch (j->G) {
+    case 4:  j->known ? dec_lane<4, true>(lane, j)  : dec_lane<4, false>(lane, j); break;
     case 8:  j->known ? dec_lane<8, true>(lane, j)  : dec_lane<8, false>(lane, j); break;
     case 16: j->known ? dec_lane<16, true>(lane, j) : dec_lane<16, false>(lane, j); break;
     default: j->known ? dec_lane<32, true>(lane, j) : dec_lane<32, false>(lane, j); break;

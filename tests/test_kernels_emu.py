@@ -81,7 +81,7 @@ def test_encode_schedule_independent():
         _enc_check(blocks, sched_seed=seed)
 
 
-@pytest.mark.parametrize("lanes", [32, 16, 8, 132, 116, 108])
+@pytest.mark.parametrize("lanes", [32, 16, 8, 4, 132, 116, 108, 104])
 @pytest.mark.parametrize("known", [True, False])
 def test_decode_matches_oracle(lanes, known):
     blocks, raws = [], []
@@ -164,6 +164,6 @@ def test_decode_long_overlapping_matches():
         pat = rng.integers(0, 256, off, dtype=np.uint8)
         raws.append(np.tile(pat, 9000 // off + 2)[:9000].tobytes())
     comp = [oracle.encode(d)[1] for d in raws]
-    for lanes in (32, 16, 8, 132, 116, 108):
+    for lanes in (32, 16, 8, 4, 132, 116, 108, 104):
         res, outs = emu.decode(comp, [len(d) for d in raws], lanes=lanes, known=True, sched_seed=lanes)
         assert outs == raws
