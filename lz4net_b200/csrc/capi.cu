@@ -32,7 +32,7 @@ int cuda_fail(cudaError_t e, const char* what)
 
 constexpr int NSLOT = 3;                       // pipeline depth of host-memory batches
 constexpr int NCOUNTER = 256;
-constexpr size_t HOST_CHUNK_BYTES_DEFAULT = 256u << 20; // src + dst bytes per pipeline stage
+constexpr size_t HOST_CHUNK_BYTES_DEFAULT = 128u << 20; // src + dst bytes per pipeline stage (tools/e2e_sweep.py: 128 MiB is the best of 32..512 on B200)
 
 struct DevBuf {
     void* p = nullptr; size_t cap = 0;
