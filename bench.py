@@ -331,7 +331,7 @@ def main():
     ctx = lz4net_b200.Context(local)
     # decode group size per entropy class (tools/sweep.py, profiles/sweep_r01.txt): lanes per block, +100 = the
     # shared-memory output-staged variant.  Long-run data wants whole warps, sequence-dense data sub-warp groups.
-    TUNED_LANES = {"E0": 32, "E50": 108, "E100": 16, "ETEXT": 8}
+    TUNED_LANES = {"E0": 32, "E50": 108, "E100": 16, "ETEXT": 104}
     lanes_for = lambda cls: args.lanes or TUNED_LANES[cls]
     ctx.set_option("decode_lanes", lanes_for(args.cls))
     if args.enc_ctas:

@@ -127,8 +127,12 @@ int lz4b200_unwrap(lz4b200_ctx* ctx, const void* src, int32_t n, void* dst, int3
 int lz4b200_synth_fill(lz4b200_ctx* ctx, void* dst, int64_t n_blocks, int32_t block_size, int cls, uint64_t seed,
                        int64_t first_block, void* stream);
 
-/* Tuning knobs (bench / profiling only).  key: "decode_lanes" (8|16|32 lanes per block), "encode_ctas_per_sm",
- * "hc_concurrency" (blocks in flight), "host_chunk_mb" (bytes per pipeline stage of host-memory batches).  Returns LZ4B200_OK or LZ4B200_E_ARG. */
+/* Tuning knobs (bench / profiling only).  key: "decode_lanes" (4|8|16|32 lanes per block, +100 = the output-staged
+ * variant), "decode_lanes_auto" (host batches pick the group size from the compression ratio), "encode_ctas_per_sm"
+ * (encoder warps = blocks in flight per SM, 0 = as many as shared memory allows: 14), "encode_variant" (1 = always
+ * exact same-hash votes, 2 = resolved through the table: default; +10 = candidate probes through L2 only),
+ * "encode_prefetch" (bytes of input kept prefetched ahead of the parse; 0 off, < 0 L2 only), "hc_concurrency" (blocks
+ * in flight), "host_chunk_mb" (bytes per pipeline stage of host-memory batches).  Returns LZ4B200_OK or LZ4B200_E_ARG. */
 int lz4b200_set_option(lz4b200_ctx* ctx, const char* key, int64_t value);
 
 /* Kernel launches issued through this context since creation (bench.py reports it as gpu_launches). */

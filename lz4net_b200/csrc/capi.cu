@@ -83,7 +83,7 @@ struct lz4b200_ctx {
     bool decode_lanes_auto = true;         // host-memory batches: chosen per chunk from the compression ratio
     int encode_ctas_per_sm = 0;            // 0 = as many as shared memory allows
     int encode_variant = 2;                // same-hash detection inside a round: 1 exact votes, 2 optimistic (default)
-    int encode_prefetch = 1024;            // bytes of input kept prefetched ahead of the parse (> 0: L1, < 0: L2 only, 0: off)
+    int encode_prefetch = 512;             // bytes of input kept prefetched ahead of the parse (> 0: L1, < 0: L2 only, 0: off)
     size_t host_chunk_bytes = HOST_CHUNK_BYTES_DEFAULT;
     int hc_concurrency = 65536;          // blocks in flight (one thread each, 256 KiB state): measured 3x over 16384
     Slot slot[NSLOT];

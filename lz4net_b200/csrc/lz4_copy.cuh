@@ -72,6 +72,7 @@ struct InWords {
 // Ring in shared memory: byte i of the source lives at buf[(pos0 + i) & (SIZE-1)].
 template <int SIZE>
 struct RingSrc {
+    static constexpr bool PIPELINED = false;
     const uint8_t* buf; uint32_t pos0;
     SIMT_MEM uint8_t byte(uint32_t i) const { return buf[(pos0 + i) & (SIZE - 1)]; }
     SIMT_MEM uint32_t misalign(uint32_t i) const { return (pos0 + i) & 15; }
@@ -83,6 +84,7 @@ struct RingSrc {
 };
 // Global memory written earlier by this same group (decoder back-references): coherent loads.
 struct GlobalSrc {
+    static constexpr bool PIPELINED = false;
     const uint8_t* p;
     SIMT_MEM uint8_t byte(uint32_t i) const { return simt::ldg_u8(p + i); }
     SIMT_MEM uint32_t misalign(uint32_t i) const { return (uint32_t)((uintptr_t)(p + i) & 15); }
@@ -93,6 +95,7 @@ struct GlobalSrc {
 };
 // Global memory that is a kernel input (encoder literals): read-only path.
 struct InputSrc {
+    static constexpr bool PIPELINED = true;
     const uint8_t* p;
     SIMT_MEM uint8_t byte(uint32_t i) const { return simt::ldg_nc_u8(p + i); }
     SIMT_MEM uint32_t misalign(uint32_t i) const { return (uint32_t)((uintptr_t)(p + i) & 15); }
@@ -123,7 +126,27 @@ SIMT_DEV void group_copy(uint8_t* dst, const Src& src, uint32_t n, int lane, uin
     if (SYNC_EACH) simt::syncwarp(gmask);
     const uint32_t nvec = (n - head) >> 4;
     const uint32_t r = src.misalign(head);
-    for (uint32_t v0 = 0; v0 < nvec; v0 += G) {
+    uint32_t v0 = 0;
+    if (!SYNC_EACH && Src::PIPELINED) {
+        // long runs: four vectors per lane per iteration, all loads issued before the first store (one memory round
+        // trip per 4 * 16 * G bytes instead of one per 16 * G -- it matters when few warps are resident: the encoders; measured
+        // slower for the decoder, whose many warps hide the latency and which pays for the registers in occupancy)
+        for (; v0 + 4u * G <= nvec; v0 += 4u * G) {
+            uint4 lo[4], hi[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t i = head + ((v0 + k * G + lane) << 4);
+                lo[k] = src.word(i, 0);
+                if (r) hi[k] = src.word(i, 1);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t i = head + ((v0 + k * G + lane) << 4);
+                simt::stg_v4(dst + i, r ? shift16(lo[k], hi[k], r) : lo[k]);
+            }
+        }
+    }
+    for (; v0 < nvec; v0 += G) {
         const uint32_t v = v0 + lane;
         if (v < nvec) {
             const uint32_t i = head + (v << 4);

@@ -60,6 +60,14 @@ SIMT_DEV uint32_t hash_peers(uint32_t h, bool valid, uint32_t vmask, int lane)
     return valid ? m : (1u << lane);
 }
 
+// A long literal run (> 32 bytes), copied by the whole warp with pipelined 128-bit moves.  Kept out of line: it is the
+// rare path of the emission, and inlined its eight vector registers pairs would spill the parse loop.
+SIMT_NOINLINE void copy_long_literals(uint8_t* dst, const uint8_t* src, uint32_t n, int lane)
+{
+    InputSrc sp{src};
+    group_copy<32, false>(dst, sp, n, lane, 0xFFFFFFFFu);
+}
+
 // The position table behind a 32-bit shared-window address.
 template <bool GENERAL>
 struct EncTable {
@@ -306,9 +314,9 @@ SIMT_DEV int encode_block_t(EncShared* sh, const uint8_t* src, int n, uint8_t* d
             } else {
 #pragma unroll 1
                 for (int i = s; i < s + 4 && i < q; i++) {
-                    InputSrc sp{src + (int)simt::shfl(FULL, (uint32_t)sq_anchor, i)};
+                    const uint8_t* const sp = src + (int)simt::shfl(FULL, (uint32_t)sq_anchor, i);
                     uint8_t* const dp = dst + (int)simt::shfl(FULL, (uint32_t)litpos, i);
-                    group_copy<32, false>(dp, sp, simt::shfl(FULL, (uint32_t)Lq, i), lane, FULL);
+                    copy_long_literals(dp, sp, simt::shfl(FULL, (uint32_t)Lq, i), lane);
                 }
             }
         }
@@ -393,22 +401,31 @@ SIMT_DEV int encode_block_t(EncShared* sh, const uint8_t* src, int n, uint8_t* d
                 cnt = x ? (simt::ffs(x) - 1) >> 3 : 4;
                 if (cnt > room) cnt = room;
             }
-            for (;;) {
-                const uint32_t part = simt::ballot(FULL, cnt != 4);
-                if (part) {
-                    const int pl = simt::ffs(part) - 1;
-                    mp += 4 * pl + (int)simt::shfl(FULL, (uint32_t)cnt, pl);
-                    break;
+            {
+                uint32_t part = simt::ballot(FULL, cnt != 4);
+                while (!part) {
+                    // the first 128 bytes all matched: a long match.  Count 512 bytes per step, every load before the
+                    // first vote (one memory round trip per 512 bytes)
+                    mp += 128; mr += 128;
+                    constexpr int NC = 4;
+                    int c4[NC];
+#pragma unroll
+                    for (int k = 0; k < NC; k++) {
+                        const int a = mp + 128 * k + 4 * lane;
+                        int room = matchlimit - a; room = room < 0 ? 0 : (room > 4 ? 4 : room);
+                        const uint32_t x = InWords::word(in.raw<0>(room > 0 ? a : 0)) ^ InWords::word(in.raw<LDP>(room > 0 ? mr + 128 * k + 4 * lane : 0));
+                        c4[k] = x ? (simt::ffs(x) - 1) >> 3 : 4;
+                        if (c4[k] > room) c4[k] = room;
+                    }
+#pragma unroll
+                    for (int k = 0; k < NC; k++) {
+                        if (part) break;
+                        part = simt::ballot(FULL, c4[k] != 4);
+                        if (part) cnt = c4[k]; else if (k < NC - 1) { mp += 128; mr += 128; }
+                    }
                 }
-                mp += 128; mr += 128;
-                const int a = mp + 4 * lane;
-                int room = matchlimit - a; room = room < 0 ? 0 : (room > 4 ? 4 : room);
-                cnt = 0;
-                if (room > 0) {
-                    const uint32_t x = in.at(a) ^ in.at(mr + 4 * lane);
-                    cnt = x ? (simt::ffs(x) - 1) >> 3 : 4;
-                    if (cnt > room) cnt = room;
-                }
+                const int pl = simt::ffs(part) - 1;
+                mp += 4 * pl + (int)simt::shfl(FULL, (uint32_t)cnt, pl);
             }
             // ---------------- park the sequence ----------------
             const int L = ip - anchor;

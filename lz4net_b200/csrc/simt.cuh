@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 #define SIMT_DEV __device__ __forceinline__
 #define SIMT_MEM __device__ __forceinline__
+#define SIMT_NOINLINE __device__ __noinline__
 
 namespace simt {
 

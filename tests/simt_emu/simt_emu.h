@@ -69,3 +69,4 @@ static inline void fence_mbar_init() {}
 }
 #define SIMT_DEV static inline
 #define SIMT_MEM inline
+#define SIMT_NOINLINE static

@@ -43,6 +43,33 @@ def test_encode_fast_byte_identical(ctx):
         assert (r, o) == oracle.encode(b), len(b)
 
 
+@pytest.mark.parametrize("variant", [1, 11, 12, 2])
+def test_encode_fast_kernel_variants(ctx, variant):
+    """Every form of the round (always-exact votes / resolved through the table, candidate probes through L1 / L2 only)
+    emits the same bytes: lz4net's.  Also with fewer encoder warps per SM and the prefetch off."""
+    blocks = _inputs(lens=[65536, 65546, 4097, 13, 70000])
+    ctx.set_option("encode_variant", variant)
+    ctx.set_option("encode_ctas_per_sm", 5 if variant == 11 else 0)
+    ctx.set_option("encode_prefetch", 0 if variant == 12 else 512)
+    try:
+        res, outs = ctx.encode_blocks(blocks)
+    finally:
+        ctx.set_option("encode_variant", 2); ctx.set_option("encode_ctas_per_sm", 0); ctx.set_option("encode_prefetch", 512)
+    for b, r, o in zip(blocks, res, outs):
+        assert (r, o) == oracle.encode(b), (variant, len(b))
+
+
+def test_encode_output_limit_inside_every_emission_batch(ctx):
+    """The encoder checks the reference's output limits for 32 parked sequences at a time: sweep the capacity across a
+    whole block so that the first failing sequence falls at every position of such a batch."""
+    d = cases.content("ETEXT", 3000, seed=5).tobytes()
+    r, _ = oracle.encode(d)
+    caps = list(range(0, r + 3))
+    res, outs = ctx.encode_blocks([d] * len(caps), caps=caps)
+    for cap, rr, o in zip(caps, res, outs):
+        assert (rr, o) == oracle.encode(d, cap=cap), cap
+
+
 def test_encode_hc_byte_identical(ctx):
     blocks = _inputs(lens=[65536, 40000, 65546, 20, 12, 0, 100000])
     res, outs = ctx.encode_blocks(blocks, hc=True)
@@ -87,7 +114,7 @@ def test_golden_vectors(ctx):
             assert r2 == c[mode]["len_cap_n"], (c["name"], mode)
 
 
-@pytest.mark.parametrize("lanes", [32, 16, 8, 132, 116, 108])
+@pytest.mark.parametrize("lanes", [32, 16, 8, 4, 132, 116, 108, 104])
 @pytest.mark.parametrize("known", [True, False])
 def test_decode_bit_exact(ctx, lanes, known):
     ctx.set_option("decode_lanes", lanes)
@@ -398,3 +425,48 @@ def test_hc_host_batch_many_small_chunks(ctx):
         ctx.set_option("host_chunk_mb", 256)
     for b, r, o in zip(blocks, res, outs):
         assert (r, o) == oracle.encode_hc(b)
+
+
+@pytest.mark.parametrize("cls", ["E50", "ETEXT"])
+def test_large_batch_properties(ctx, cls):
+    """Size-independent properties on a batch the oracle could not finish in seconds (65 536 blocks = 4 GiB): the
+    round trip is exact for every decoder group size, every stream is consumed exactly, the per-block sizes are
+    identical across encoder variants, and a checksum of the compressed bytes of 64 sampled blocks equals the oracle's."""
+    import torch
+    from lz4net_b200 import batch, synth
+    nb, bs = 65536, 65536
+    slot = oracle.bound(bs)
+    raw = torch.empty(nb * bs, dtype=torch.uint8, device="cuda")
+    for b0 in range(0, nb, 16384):
+        batch.synth_fill(ctx, raw[b0 * bs:], 16384, bs, synth.CLASS_ID[cls], seed=9, first_block=b0)
+    so, do, sl, dc = batch.uniform_layout(nb, bs, slot, "cuda")
+    slots = torch.empty(nb * slot, dtype=torch.uint8, device="cuda")
+    clen = torch.zeros(nb, dtype=torch.int32, device="cuda")
+    batch.encode(ctx, raw, so, sl, slots, do, dc, clen)
+    ctx.set_option("encode_variant", 1)
+    clen1 = torch.zeros(nb, dtype=torch.int32, device="cuda")
+    slots1 = torch.empty(nb * slot, dtype=torch.uint8, device="cuda")
+    try:
+        batch.encode(ctx, raw, so, sl, slots1, do, dc, clen1)
+    finally:
+        ctx.set_option("encode_variant", 2)
+    torch.cuda.synchronize()
+    assert int((clen <= 0).sum()) == 0 and torch.equal(clen, clen1)
+    del slots1
+    out = torch.empty(nb * bs, dtype=torch.uint8, device="cuda")
+    used = torch.zeros(nb, dtype=torch.int32, device="cuda")
+    try:
+        for lanes in (32, 16, 108, 104):
+            ctx.set_option("decode_lanes", lanes)
+            out.zero_()
+            batch.decode(ctx, slots, do, clen, out, so, sl, used, known=True)
+            torch.cuda.synchronize()
+            assert torch.equal(used, clen) and torch.equal(out, raw), lanes
+    finally:
+        ctx.set_option("decode_lanes", 16)
+    idx = list(range(0, nb, nb // 64))
+    h_len = clen.cpu().numpy()
+    for i in idx:
+        r, o = oracle.encode(raw[i * bs:(i + 1) * bs].cpu().numpy().tobytes())
+        got = slots[i * slot:i * slot + int(h_len[i])].cpu().numpy().tobytes()
+        assert h_len[i] == r and hashlib.sha256(got).digest() == hashlib.sha256(o).digest(), i

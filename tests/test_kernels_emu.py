@@ -49,6 +49,16 @@ def test_encode_limited_output():
     _enc_check(blocks, caps, sched_seed=3)
 
 
+def test_encode_output_limit_inside_every_emission_batch():
+    """The encoder evaluates the reference's output-limit checks for 32 parked sequences at a time: sweep the capacity
+    over the whole compressed size so that the first failing sequence falls at every position of such a batch."""
+    for model, n in (("ETEXT", 1500), ("lowent", 1200), ("E50", 2500)):
+        d = cases.content(model, n, seed=5).tobytes()
+        r, _ = oracle.encode(d)
+        caps = list(range(0, r + 3))
+        _enc_check([d] * len(caps), caps, sched_seed=8)
+
+
 def test_encode_general_variant_above_64k():
     """n >= 65547 takes LZ4_compressCtx (original/lz4.c:345-562): 12-bit hash, u32 table, distance checks."""
     blocks = [cases.content(m, n, seed=7).tobytes()
