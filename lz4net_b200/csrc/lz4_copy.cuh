@@ -61,6 +61,9 @@ struct InWords {
     {
         const uint32_t q = (uint32_t)p + sk, i = q >> 2;
         Raw r; r.sh = (q & 3u) * 8u;
+        // Both words unconditionally (no predicate on the critical path).  Callers only pass positions p <= n - 6 (probe
+        // positions <= n - 13, match-count positions < n - 5), so word i + 1 always holds the input byte p + 4: no word
+        // without an input byte is ever touched (tests/test_kernels_emu.py::test_encode_never_reads_past_the_input).
         if (POLICY == 1) { r.lo = simt::ldg_cg_u32(w + i); r.hi = simt::ldg_cg_u32(w + i + 1); }
         else             { r.lo = simt::ldg_nc_u32(w + i); r.hi = simt::ldg_nc_u32(w + i + 1); }
         return r;

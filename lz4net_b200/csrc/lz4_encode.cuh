@@ -368,6 +368,11 @@ SIMT_DEV int encode_block_t(EncShared* sh, const uint8_t* src, int n, uint8_t* d
                 if (r.f < 0) { r.f = 32; consumed = 32; }           // exact path: only the first 32 iterations were evaluated
                 if (r.f >= consumed) {                              // no hit: the find-match loop goes on
                     A0 += (uint32_t)consumed; fused = false; wide = true;
+                    if (tune.pf_dist != 0) {                        // incompressible stretch: fetch what the round after next will read
+                        const uint32_t qa = A0 >> 6;
+                        const int p = org + (int)(qa * (((qa - 1u) << 5) + (A0 & 63u))) + 64 * (int)qa + 128 * lane;
+                        if (lane < 8 && p < n) { if (tune.pf_dist > 0) simt::prefetch_l1(src + p); else simt::prefetch_l2(src + p); }
+                    }
                     continue;
                 }
                 if (r.finished) { finished = true; break; }
@@ -407,6 +412,7 @@ SIMT_DEV int encode_block_t(EncShared* sh, const uint8_t* src, int n, uint8_t* d
                     // the first 128 bytes all matched: a long match.  Count 512 bytes per step, every load before the
                     // first vote (one memory round trip per 512 bytes)
                     mp += 128; mr += 128;
+                    if (tune.pf_dist != 0 && lane < 4 && mp + 1024 + 128 * lane < n) simt::prefetch_l1(src + mp + 1024 + 128 * lane);
                     constexpr int NC = 4;
                     int c4[NC];
 #pragma unroll

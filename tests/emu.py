@@ -101,3 +101,35 @@ def encode_hc(block, cap=None, src_skew=0):
     r = lib().emu_encode_hc(C.c_void_p(a.ctypes.data + src_skew), n, C.c_void_p(d.ctypes.data + 32), cap)
     assert (d[:32] == 0xCD).all() and (d[32 + max(cap, 0):] == 0xCD).all(), "HC encoder wrote outside [dst, dst+cap)"
     return int(r), d[32:32 + max(r, 0)].tobytes()
+
+
+def encode_guarded(block, sched_seed=1, variant=2, end_pad=0):
+    """Encode one block whose last byte is the last byte of a readable page: the page after it is PROT_NONE, so any
+    read of a word that holds no input byte (an over-read past the end of the input) kills the process with SIGSEGV.
+    end_pad (0..3) bytes stay readable behind the block: the rest of its last aligned 32-bit word (the kernels read whole
+    aligned words).  Returns (result, bytes)."""
+    import mmap
+    page = mmap.PAGESIZE
+    n = len(block)
+    assert 0 <= end_pad < 4
+    npages = (n + page - 1) // page + 1
+    m = mmap.mmap(-1, (npages + 1) * page)
+    base = C.addressof(C.c_char.from_buffer(m))
+    libc = C.CDLL(None, use_errno=True)
+    libc.mprotect.argtypes = [C.c_void_p, C.c_size_t, C.c_int]
+    assert libc.mprotect(base + npages * page, page, 0) == 0
+    start = npages * page - n - end_pad
+    assert (start + n + 3) // 4 * 4 <= npages * page
+    m[start:start + n] = block
+    cap = n + n // 255 + 16
+    dst = np.full(cap + 96, 0xCD, np.uint8)
+    ns = np.array([n], np.int32); cps = np.array([cap], np.int32); res = np.zeros(1, np.int32)
+    sp = (C.c_void_p * 1)(base + start); dp = (C.c_void_p * 1)(dst.ctypes.data + 32)
+    lib().emu_set_encode_variant(variant)
+    lib().emu_encode(1, sp, ns.ctypes.data_as(C.c_void_p), dp, cps.ctypes.data_as(C.c_void_p), res.ctypes.data_as(C.c_void_p),
+                     C.c_uint64(sched_seed))
+    r = int(res[0])
+    out = dst[32:32 + max(r, 0)].tobytes()
+    assert libc.mprotect(base + npages * page, page, 3) == 0
+    del sp
+    return r, out
