@@ -57,7 +57,7 @@ def parse():
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--sweep-blocks", type=int, default=1 << 17)
-    p.add_argument("--hc-blocks", type=int, default=1 << 16)
+    p.add_argument("--hc-blocks", type=int, default=1 << 17)
     return p.parse_args()
 
 

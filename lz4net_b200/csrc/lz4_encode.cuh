@@ -184,6 +184,7 @@ SIMT_DEV RoundOut find_round(const EncTable<GENERAL>& T, const InWords& in, int 
         int nv = simt::popc(vmask[0]), fh = hitm[0] ? simt::ffs(hitm[0]) - 1 : 64;
         if (W == 2) { nv += simt::popc(vmask[W - 1]); if (!hitm[0] && hitm[W - 1]) fh = 32 + simt::ffs(hitm[W - 1]) - 1; }
         const int f = fh < nv ? fh : nv;                            // == 32*W: nothing happened in this round
+        simt::syncwarp(FULL);                                      // every lane's read-backs are done before any bucket is rewritten
         // final bucket values: the last sharer whose iteration ran (index <= f) leaves its position, else the old entry.
         // Without a partner I write either way; of two sharers the later one writes if it ran, the earlier one if the
         // later one did not (its own position if it ran itself, else the old entry).
