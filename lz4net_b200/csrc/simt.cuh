@@ -23,6 +23,9 @@ SIMT_DEV uint32_t ballot(uint32_t mask, bool p) { return __ballot_sync(mask, p);
 SIMT_DEV uint32_t match_any(uint32_t mask, uint32_t v) { return __match_any_sync(mask, v); }
 SIMT_DEV uint32_t reduce_max(uint32_t mask, uint32_t v) { return __reduce_max_sync(mask, v); }     // REDUX
 SIMT_DEV void syncwarp(uint32_t mask) { __syncwarp(mask); }
+// Lanes of the warp that are executing this instruction together right now (a superset of the caller's own group
+// `own`).  For opportunistic co-scheduling of work that is valid at any time for every group (never for correctness).
+SIMT_DEV uint32_t converged(uint32_t own) { return __activemask() | own; }
 SIMT_DEV int ffs(uint32_t v) { return __ffs((int)v); }
 SIMT_DEV int clz(uint32_t v) { return __clz((int)v); }
 SIMT_DEV int popc(uint32_t v) { return __popc(v); }

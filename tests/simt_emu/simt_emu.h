@@ -29,6 +29,7 @@ static inline uint32_t shfl(uint32_t mask, uint32_t v, int src) { return simt_em
 static inline uint32_t ballot(uint32_t mask, bool p) { return simt_emu::collective(simt_emu::OP_BALLOT, mask, p ? 1u : 0u, 0); }
 static inline uint32_t match_any(uint32_t mask, uint32_t v) { return simt_emu::collective(simt_emu::OP_MATCH, mask, v, 0); }
 static inline uint32_t reduce_max(uint32_t mask, uint32_t v) { return simt_emu::collective(simt_emu::OP_RMAX, mask, v, 0); }
+static inline uint32_t converged(uint32_t own) { return own; }     // the emulator's lanes are never known to be converged beyond their group
 static inline void syncwarp(uint32_t mask) { simt_emu::collective(simt_emu::OP_SYNC, mask, 0, 0); }
 static inline int ffs(uint32_t v) { return __builtin_ffs((int)v); }
 static inline int clz(uint32_t v) { return v ? __builtin_clz(v) : 32; }
