@@ -108,11 +108,12 @@ struct DecStream {
     // contiguous from ring offset (ip + rot) & (RING-1); limit >= ip + DEC_AHEAD unless the stream ends first.
     // Only the chunk that the next DEC_AHEAD bytes reach into is waited for, so a chunk is first touched about three
     // chunk-times after its bulk copy was launched (fill keeps chunks c .. c+3 in flight).
-    SIMT_MEM int window(int ip, int isize)
+    // `extra` > 0 (<= CHUNK) looks that much further ahead, so that groups sliding together stay together for a while.
+    SIMT_MEM int window(int ip, int isize, int extra = 0)
     {
         const int c = chunk_of((uint32_t)ip);
         fill(c);
-        int last = chunk_of((uint32_t)(ip + DEC_AHEAD)); if (last > nchunks - 1) last = nchunks - 1;
+        int last = chunk_of((uint32_t)(ip + DEC_AHEAD + extra)); if (last > nchunks - 1) last = nchunks - 1;
         wait_chunk(last);
         const int lim = (int)(((uint32_t)(last + 1) << LOG_CHUNK) - skew);
         return lim < isize ? lim : isize;
@@ -374,7 +375,11 @@ SIMT_DEV int decode_block_staged(DecStream<G>& st, DecStage<G>* stage, const uin
     const int out_fast = cap - (FAST_L + FAST_M + 16);
     int in_fast = st.window(0, isize) - DEC_AHEAD;
     for (;;) {
-        if (cur.ip > in_fast) in_fast = st.window(cur.ip, isize) - DEC_AHEAD;
+        // Slide the input window when this group needs it -- or when a group running in lock step with it slides anyway
+        // (same argument as for the flushes below: a refill executed by one group alone costs the warp as much as one
+        // executed by all).  Everybody then looks one chunk further ahead, so the groups stay together for a while.
+        if (simt::ballot(simt::converged(gmask), cur.ip > in_fast))
+            in_fast = st.window(cur.ip, isize, DecGeom<G>::CHUNK) - DEC_AHEAD;
         if (cur.ip <= in_fast && cur.op <= out_fast) {
             const uint8_t* const h = rb + (((uint32_t)cur.ip + rot) & (RING - 1));
             // branch-free header parse: both possible length bytes are loaded unconditionally (they are inside the
