@@ -56,3 +56,50 @@ def test_ranges():
             assert all(rs[i][1] == rs[i + 1][0] for i in range(world - 1))
             sizes = [b - a for a, b in rs]
             assert max(sizes) - min(sizes) <= 1
+
+
+# ---- one stream, many ranks (BASELINE configs[3]): scatter from the root, encode per rank, gather in stream order ------
+def _toy_codec(bs):
+    """A stand-in codec for the CPU test of the plumbing: a block is 'compressed' by dropping its trailing zero bytes."""
+    def enc(raw, m):
+        blocks = raw.view(m, bs)
+        lens = torch.tensor([max(1, int(torch.nonzero(b).max().item()) + 1 if bool(b.any()) else 1) for b in blocks], dtype=torch.int32)
+        return torch.cat([b[:int(n)] for b, n in zip(blocks, lens)]), lens
+
+    def dec(packed, lens, m):
+        out = torch.zeros(m * bs, dtype=torch.uint8)
+        p = 0
+        for i, n in enumerate(lens.tolist()):
+            out[i * bs:i * bs + n] = packed[p:p + n]; p += n
+        return out
+    return enc, dec
+
+
+def _stream_worker(rank, world, port, n_blocks, bs, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    enc, dec = _toy_codec(bs)
+    raw = None
+    if rank == 0:
+        g = torch.Generator().manual_seed(5)
+        raw = torch.randint(0, 256, (n_blocks * bs,), dtype=torch.uint8, generator=g)
+        for i in range(n_blocks):                                  # zero tails of different lengths -> different payload sizes
+            raw[i * bs + (37 * i) % bs + 1:(i + 1) * bs] = 0
+    lens, off, packed = shard.encode_stream_sharded(raw, n_blocks, bs, enc, rank, world)
+    if rank == 0:
+        want_p, want_l = enc(raw, n_blocks)                        # the same stream through one rank
+        assert torch.equal(lens, want_l) and torch.equal(packed, want_p)
+        assert off.tolist() == [0] + torch.cumsum(want_l.to(torch.int64), 0).tolist()
+    back = shard.decode_stream_sharded(packed, lens, n_blocks, bs, dec, rank, world)
+    if rank == 0:
+        assert torch.equal(back, raw)
+        open(os.path.join(out_dir, "ok"), "w").write("1")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_blocks", [(2, 7), (3, 2), (2, 1)])
+def test_stream_scatter_encode_gather_gloo(tmp_path, world, n_blocks):
+    """More ranks than blocks, uneven splits, one block: order and bytes are those of the single-rank result."""
+    mp.spawn(_stream_worker, args=(world, _free_port(), n_blocks, 64, str(tmp_path)), nprocs=world, join=True)
+    assert (tmp_path / "ok").exists()
