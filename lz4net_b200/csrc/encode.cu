@@ -29,15 +29,15 @@ lz4_encode_fast_kernel(BatchArgs a, uint32_t* counter, EncTune tune)
 }
 
 template <int DUP, int LDP>
-static cudaError_t launch_fast_t(const BatchArgs& a, uint32_t* counter, int dyn, long long grid, int warps, int prefetch, cudaStream_t stream)
+static cudaError_t launch_fast_t(const BatchArgs& a, uint32_t* counter, int dyn, long long grid, int warps, const EncTune& tune, cudaStream_t stream)
 {
     cudaError_t e = cudaFuncSetAttribute(lz4_encode_fast_kernel<DUP, LDP>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
     if (e != cudaSuccess) return e;
-    lz4_encode_fast_kernel<DUP, LDP><<<(unsigned)grid, 32 * warps, dyn, stream>>>(a, counter, EncTune{prefetch});
+    lz4_encode_fast_kernel<DUP, LDP><<<(unsigned)grid, 32 * warps, dyn, stream>>>(a, counter, tune);
     return cudaGetLastError();
 }
 
-cudaError_t launch_encode_fast(const BatchArgs& a, uint32_t* counter, int warps_per_sm, int prefetch, int variant,
+cudaError_t launch_encode_fast(const BatchArgs& a, uint32_t* counter, int warps_per_sm, const int* tune4, int variant,
                                const DeviceInfo& dev, cudaStream_t stream, int64_t* launches)
 {
     if (a.n_blocks <= 0) return cudaSuccess;
@@ -56,12 +56,13 @@ cudaError_t launch_encode_fast(const BatchArgs& a, uint32_t* counter, int warps_
     cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), stream);
     if (e != cudaSuccess) return e;
     if (launches) ++*launches;
+    EncTune tune; tune.pf_dist = tune4[0]; tune.lane_copy_max = tune4[1]; tune.probe_max = tune4[2]; tune.wide_min = tune4[3];
     switch (variant) {                      // variant % 10: how same-hash iterations of one round are found (lz4_encode.cuh);
                                             // variant / 10: candidate loads through L1 (0) or L2 only (1)
-    case 1:  return launch_fast_t<1, 0>(a, counter, dyn, grid, warps, prefetch, stream);  // always exact: one vote per hash bit
-    case 11: return launch_fast_t<1, 1>(a, counter, dyn, grid, warps, prefetch, stream);
-    case 12: return launch_fast_t<2, 1>(a, counter, dyn, grid, warps, prefetch, stream);
-    default: return launch_fast_t<2, 0>(a, counter, dyn, grid, warps, prefetch, stream);  // through the table, pairs resolved in place
+    case 1:  return launch_fast_t<1, 0>(a, counter, dyn, grid, warps, tune, stream);  // always exact: one vote per hash bit
+    case 11: return launch_fast_t<1, 1>(a, counter, dyn, grid, warps, tune, stream);
+    case 12: return launch_fast_t<2, 1>(a, counter, dyn, grid, warps, tune, stream);
+    default: return launch_fast_t<2, 0>(a, counter, dyn, grid, warps, tune, stream);  // through the table, pairs resolved in place
     }
 }
 

@@ -41,7 +41,13 @@ struct alignas(16) EncShared { uint32_t table[4096]; };
 
 constexpr int LZ4_64KLIMIT = 65547;                                // original/lz4.c:565
 
-struct EncTune { int pf_dist; };                                   // > 0: L1 prefetch that many bytes ahead; < 0: L2; 0: off
+// Heuristics that only steer which (equivalent) code path runs -- never the emitted bytes.
+struct EncTune {
+    int pf_dist = 0;          // > 0: L1 prefetch that many bytes ahead; < 0: L2; 0: off
+    int lane_copy_max = 12;   // emission: every lane copies its own literal run when all 32 runs are at most this long
+    int probe_max = 8;        // after a literal run shorter than this, the post-match probe is tried alone before a round
+    int wide_min = 24;        // after a literal run at least this long, the fused round is 64 iterations wide
+};
 
 // flags kept above the 16-bit offset of a parked sequence
 constexpr uint32_t SEQ_NOCHK = 0x10000u;                           // zero-literal `goto _next_match` sequence: no :663 check
@@ -293,7 +299,7 @@ SIMT_DEV int encode_block_t(EncShared* sh, const uint8_t* src, int n, uint8_t* d
         // iterations for 32 sequences.  Otherwise the whole warp copies run after run, four short runs per step.
         const int Lq = act ? L : 0;
         const int Lmax = (int)simt::reduce_max(FULL, (uint32_t)Lq);
-        if (Lmax <= 12) {
+        if (Lmax <= tune.lane_copy_max) {
             const uint8_t* sp = src + sq_anchor; uint8_t* dp = dst + litpos;
             for (int i = 0; i < Lq; i++) simt::stg_u8(dp + i, simt::ldg_nc_u8(sp + i));
         } else
@@ -451,9 +457,9 @@ SIMT_DEV int encode_block_t(EncShared* sh, const uint8_t* src, int n, uint8_t* d
             // What follows a match (:519-534 / :739-755): insert ip-2, probe + insert ip, then the find-match loop from
             // ip+1.  Short literal runs predict another immediate hit: do the probe alone first.  Otherwise all of it
             // is one fused round: attempts 65, 66 = ip-2, ip; 67.. = the loop.  S(66) = 2, so org = mp - 2.
-            probe_first = L < 8;
+            probe_first = L < tune.probe_max;
             org = mp - 2; A0 = 65; fused = true;
-            wide = L >= 24;                                         // long literal runs: the next match is probably > 30 bytes away
+            wide = L >= tune.wide_min;                                      // long literal runs: the next match is probably > 30 bytes away
         }
     }
 
@@ -466,7 +472,7 @@ SIMT_DEV int encode_block_t(EncShared* sh, const uint8_t* src, int n, uint8_t* d
 
 // LZ4_compress_limitedOutput dispatch (original/lz4.c:774-792)
 template <int DUP = 2, int LDP = 0>
-SIMT_DEV int encode_block(EncShared* sh, const uint8_t* src, int n, uint8_t* dst, int cap, int lane, EncTune tune = EncTune{0})
+SIMT_DEV int encode_block(EncShared* sh, const uint8_t* src, int n, uint8_t* dst, int cap, int lane, EncTune tune = EncTune{})
 {
     if (n < 0 || cap < 0) return 0;
     simt::syncwarp(0xFFFFFFFFu);                                   // previous block's table users are done

@@ -64,7 +64,7 @@ def decode(blocks, caps, lanes=32, known=True, sched_seed=1, src_skew=0):
     return res.tolist(), outs
 
 
-def encode(blocks, caps=None, sched_seed=1, src_skew=0, dst_skew=0, variant=2):
+def encode(blocks, caps=None, sched_seed=1, src_skew=0, dst_skew=0, variant=2, tune=(12, 8, 24)):
     """variant: how the encoder finds same-hash lanes inside a round (1 always exact votes, 2 optimistic = the default)."""
     n = len(blocks)
     lib().emu_set_encode_variant(variant)

@@ -101,6 +101,14 @@ def test_encode_other_duplicate_detectors(variant):
     _enc_check(blocks, sched_seed=6, variant=variant)
 
 
+@pytest.mark.parametrize("tune", [(0, 0, 0), (64, 1000, 1000), (32, 0, 1000), (0, 1000, 0)])
+def test_encode_heuristics_never_change_the_bytes(tune):
+    """lane_copy_max / probe_max / wide_min only choose between equivalent code paths (per-lane or cooperative literal
+    copies, probe-first or fused round, 32 or 64 iterations per round): every extreme setting emits the oracle's bytes."""
+    blocks = [cases.content(m, n, seed=70 + i).tobytes() for i, m in enumerate(cases.MODELS) for n in (65536, 3001)]
+    _enc_check(blocks, sched_seed=7, tune=tune)
+
+
 def test_encode_schedule_independent():
     """Lanes are scheduled in different orders: the result may not depend on lock-step luck."""
     blocks = [cases.content("lowent", 20000, seed=1).tobytes(), cases.content("mixed", 20000, seed=2).tobytes()]
