@@ -130,7 +130,7 @@ int lz4b200_synth_fill(lz4b200_ctx* ctx, void* dst, int64_t n_blocks, int32_t bl
 /* Tuning knobs (bench / profiling only).  key: "decode_lanes" (4|8|16|32 lanes per block, +100 = the output-staged
  * variant), "decode_lanes_auto" (host batches pick the group size from the compression ratio), "encode_ctas_per_sm"
  * (encoder warps = blocks in flight per SM, 0 = as many as shared memory allows: 14), "encode_variant" (1 = always
- * exact same-hash votes, 2 = resolved through the table: default; +10 = candidate probes through L2 only),
+ * exact same-hash votes, 2 = resolved through the table: default; +10 = L2 residency hints: input evict-last, emitted output evict-first -- measured neutral),
  * "encode_prefetch" (bytes of input kept prefetched ahead of the parse; 0 off, < 0 L2 only), "encode_lane_copy_max" /
  * "encode_probe_max" / "encode_wide_min" (path-selection heuristics of the fast encoder, lz4_encode.cuh EncTune: they
  * never change the emitted bytes), "hc_concurrency" (blocks

@@ -58,7 +58,7 @@ cudaError_t launch_encode_fast(const BatchArgs& a, uint32_t* counter, int warps_
     if (launches) ++*launches;
     EncTune tune; tune.pf_dist = tune4[0]; tune.lane_copy_max = tune4[1]; tune.probe_max = tune4[2]; tune.wide_min = tune4[3];
     switch (variant) {                      // variant % 10: how same-hash iterations of one round are found (lz4_encode.cuh);
-                                            // variant / 10: candidate loads through L1 (0) or L2 only (1)
+                                            // variant / 10: plain read-only loads (0) or L2 residency hints (1: input evict-last, output evict-first)
     case 1:  return launch_fast_t<1, 0>(a, counter, dyn, grid, warps, tune, stream);  // always exact: one vote per hash bit
     case 11: return launch_fast_t<1, 1>(a, counter, dyn, grid, warps, tune, stream);
     case 12: return launch_fast_t<2, 1>(a, counter, dyn, grid, warps, tune, stream);

@@ -43,8 +43,8 @@ SIMT_DEV uint32_t in32(const uint8_t* src, int p)
 // The same read through a per-block word view of the input: base rounded down to 4 bytes + a 32-bit word index, so the
 // address is one IMAD.WIDE instead of a 64-bit add, align and re-add.
 struct InWords {
-    const uint32_t* w; uint32_t sk;
-    SIMT_MEM void init(const uint8_t* src) { sk = (uint32_t)((uintptr_t)src & 3); w = (const uint32_t*)(src - sk); }
+    const uint32_t* w; uint32_t sk; uint64_t keep;
+    SIMT_MEM void init(const uint8_t* src) { sk = (uint32_t)((uintptr_t)src & 3); w = (const uint32_t*)(src - sk); keep = simt::l2_policy_keep(); }
     SIMT_MEM uint32_t at(int p) const
     {
         const uint32_t q = (uint32_t)p + sk, i = q >> 2, sh = (q & 3u) * 8u;
@@ -53,8 +53,8 @@ struct InWords {
         return simt::funnel_r(lo, hi, sh);
     }
     // The same read split in two, so that the caller decides where the warp waits for the data: raw() issues the loads
-    // (POLICY 0: read-only path through L1; 1: L2 only -- for probes at random earlier positions, which would otherwise
-    // evict the forward window from L1), word() assembles the value.
+    // (POLICY 0: plain read-only path; 1: the same with an L2 evict-last hint -- the block is probed again at random
+    // positions until its parse is over), word() assembles the value.
     struct Raw { uint32_t lo, hi, sh; };
     template <int POLICY>
     SIMT_MEM Raw raw(int p) const
@@ -64,7 +64,7 @@ struct InWords {
         // Both words unconditionally (no predicate on the critical path).  Callers only pass positions p <= n - 6 (probe
         // positions <= n - 13, match-count positions < n - 5), so word i + 1 always holds the input byte p + 4: no word
         // without an input byte is ever touched (tests/test_kernels_emu.py::test_encode_never_reads_past_the_input).
-        if (POLICY == 1) { r.lo = simt::ldg_cg_u32(w + i); r.hi = simt::ldg_cg_u32(w + i + 1); }
+        if (POLICY == 1) { r.lo = simt::ldg_nc_hint_u32(w + i, keep); r.hi = simt::ldg_nc_hint_u32(w + i + 1, keep); }
         else             { r.lo = simt::ldg_nc_u32(w + i); r.hi = simt::ldg_nc_u32(w + i + 1); }
         return r;
     }

@@ -122,7 +122,7 @@ SIMT_DEV RoundOut find_round(const EncTable<GENERAL>& T, const InWords& in, int 
         if (special && lane == 0) pos[s] -= 1;                     // (the formula gives ip-1 and ip for attempts 65 and 66)
     }
 #pragma unroll
-    for (int s = 0; s < W; s++) rp[s] = in.raw<0>(valid[s] ? pos[s] : 0);
+    for (int s = 0; s < W; s++) rp[s] = in.raw<LDP>(valid[s] ? pos[s] : 0);
 #pragma unroll
     for (int s = 0; s < W; s++) vmask[s] = SIMPLE ? FULL : simt::ballot(FULL, valid[s]);
 #pragma unroll
@@ -258,6 +258,8 @@ SIMT_DEV int encode_block_t(EncShared* sh, const uint8_t* src, int n, uint8_t* d
     int sq_anchor = 0, sq_L = 0, sq_M = 0; uint32_t sq_off = 0;
 
     // ---- EMIT: write out the q queued sequences; false = the output does not fit (the reference returns 0) ----------
+    const uint64_t spol = LDP == 1 ? simt::l2_policy_stream() : 0;
+    auto st8 = [&](uint8_t* p, uint32_t v) { if (LDP == 1) simt::stg_hint_u8(p, v, spol); else simt::stg_u8(p, (uint8_t)v); };
     auto flush = [&]() -> bool {
         const bool act = lane < q;
         const int L = sq_L, M = sq_M;
@@ -285,14 +287,14 @@ SIMT_DEV int encode_block_t(EncShared* sh, const uint8_t* src, int n, uint8_t* d
         int litpos = 0;
         if (act) {
             const int lt = L < 15 ? L : 15, mt = last ? 0 : (M < 15 ? M : 15);
-            simt::stg_u8(dst + start, (uint8_t)((lt << 4) | mt));
+            st8(dst + start, (uint32_t)((lt << 4) | mt));
             int o = start + 1;
-            if (L >= 15) { int v = L - 15; for (; v >= 255; v -= 255) simt::stg_u8(dst + o++, 255); simt::stg_u8(dst + o++, (uint8_t)v); }
+            if (L >= 15) { int v = L - 15; for (; v >= 255; v -= 255) st8(dst + o++, 255u); st8(dst + o++, (uint32_t)v); }
             litpos = o; o += L;
             if (!last) {
-                simt::stg_u8(dst + o, (uint8_t)sq_off); simt::stg_u8(dst + o + 1, (uint8_t)(sq_off >> 8));       // :470 / :695
+                st8(dst + o, sq_off & 0xFFu); st8(dst + o + 1, (sq_off >> 8) & 0xFFu);       // :470 / :695
                 o += 2;
-                if (M >= 15) { int v = M - 15; for (; v >= 255; v -= 255) simt::stg_u8(dst + o++, 255); simt::stg_u8(dst + o++, (uint8_t)v); }
+                if (M >= 15) { int v = M - 15; for (; v >= 255; v -= 255) st8(dst + o++, 255u); st8(dst + o++, (uint32_t)v); }
             }
         }
         // literal runs.  All short (token-dense data): every lane copies its own run, byte by byte -- a handful of
@@ -301,7 +303,7 @@ SIMT_DEV int encode_block_t(EncShared* sh, const uint8_t* src, int n, uint8_t* d
         const int Lmax = (int)simt::reduce_max(FULL, (uint32_t)Lq);
         if (Lmax <= tune.lane_copy_max) {
             const uint8_t* sp = src + sq_anchor; uint8_t* dp = dst + litpos;
-            for (int i = 0; i < Lq; i++) simt::stg_u8(dp + i, simt::ldg_nc_u8(sp + i));
+            for (int i = 0; i < Lq; i++) st8(dp + i, simt::ldg_nc_u8(sp + i));
         } else
         for (int s = 0; s < q; s += 4) {
             int a[4], d[4], l[4];
@@ -317,7 +319,7 @@ SIMT_DEV int encode_block_t(EncShared* sh, const uint8_t* src, int n, uint8_t* d
 #pragma unroll
                 for (int i = 0; i < 4; i++) b[i] = lane < l[i] ? simt::ldg_nc_u8(src + a[i] + lane) : (uint8_t)0;
 #pragma unroll
-                for (int i = 0; i < 4; i++) if (lane < l[i]) simt::stg_u8(dst + d[i] + lane, b[i]);
+                for (int i = 0; i < 4; i++) if (lane < l[i]) st8(dst + d[i] + lane, b[i]);
             } else {
 #pragma unroll 1
                 for (int i = s; i < s + 4 && i < q; i++) {
@@ -394,7 +396,7 @@ SIMT_DEV int encode_block_t(EncShared* sh, const uint8_t* src, int n, uint8_t* d
             {
                 const int a = mp + 4 * lane;
                 int room = matchlimit - a; room = room < 0 ? 0 : (room > 4 ? 4 : room);
-                const InWords::Raw ra = in.raw<0>(room > 0 ? a : 0), rr = in.raw<LDP>(room > 0 ? mr + 4 * lane : 0);
+                const InWords::Raw ra = in.raw<LDP>(room > 0 ? a : 0), rr = in.raw<LDP>(room > 0 ? mr + 4 * lane : 0);
                 if (ip > anchor) {                                  // (never after a zero-literal probe hit: ip == anchor)
                     const int k = lane + 1;
                     const bool okb = ip - k >= anchor && ref - k >= 0;
@@ -426,7 +428,7 @@ SIMT_DEV int encode_block_t(EncShared* sh, const uint8_t* src, int n, uint8_t* d
                     for (int k = 0; k < NC; k++) {
                         const int a = mp + 128 * k + 4 * lane;
                         int room = matchlimit - a; room = room < 0 ? 0 : (room > 4 ? 4 : room);
-                        const uint32_t x = InWords::word(in.raw<0>(room > 0 ? a : 0)) ^ InWords::word(in.raw<LDP>(room > 0 ? mr + 128 * k + 4 * lane : 0));
+                        const uint32_t x = InWords::word(in.raw<LDP>(room > 0 ? a : 0)) ^ InWords::word(in.raw<LDP>(room > 0 ? mr + 128 * k + 4 * lane : 0));
                         c4[k] = x ? (simt::ffs(x) - 1) >> 3 : 4;
                         if (c4[k] > room) c4[k] = room;
                     }

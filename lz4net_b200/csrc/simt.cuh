@@ -49,9 +49,14 @@ SIMT_DEV uint4    ldg_nc_v4(const void* p) { return __ldg((const uint4*)p); }
 SIMT_DEV void stg_u8(uint8_t* p, uint8_t v) { *p = v; }
 SIMT_DEV void stg_u32(void* p, uint32_t v) { *(uint32_t*)p = v; }
 SIMT_DEV void stg_v4(void* p, uint4 v) { *(uint4*)p = v; }
-// cached in L2 only (random probes that would evict the streaming window from L1).  Measured on B200: the
-// L1::no_allocate form of the read-only load also loses the line in L2 (30x DRAM read amplification) -- not used.
-SIMT_DEV uint32_t ldg_cg_u32(const void* p) { uint32_t v; asm("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+// L2 residency hints (no extra instruction: the policy travels in the access descriptor).  keep = evict-last, for input
+// that will be probed again at random positions while its block is being parsed; stream = evict-first, for output that is
+// written once and not read back.  (Measured and dropped: `ld.global.cg` probes, -20 %; `L1::no_allocate` probes lose the
+// line in L2 as well, 30x DRAM read amplification.)
+SIMT_DEV uint64_t l2_policy_keep() { uint64_t p; asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
+SIMT_DEV uint64_t l2_policy_stream() { uint64_t p; asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
+SIMT_DEV uint32_t ldg_nc_hint_u32(const void* p, uint64_t pol) { uint32_t v; asm("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol)); return v; }
+SIMT_DEV void stg_hint_u8(uint8_t* p, uint32_t v, uint64_t pol) { asm volatile("st.global.L2::cache_hint.u8 [%0], %1, %2;" :: "l"(p), "r"(v), "l"(pol) : "memory"); }
 // Scheduling fence without an instruction: `x` formally depends on `dep`, so the first use of x (the point where the
 // warp waits for the load that produces it) cannot be scheduled before dep has been computed.
 SIMT_DEV void tie(uint32_t& x, uint32_t dep) { asm volatile("" : "+r"(x) : "r"(dep)); }

@@ -47,7 +47,10 @@ static inline uint4    ldg_nc_v4(const void* p) { return ldg_v4(p); }
 static inline void stg_u8(uint8_t* p, uint8_t v) { *p = v; }
 static inline void stg_u32(void* p, uint32_t v) { memcpy(p, &v, 4); }
 static inline void stg_v4(void* p, uint4 v) { memcpy(p, &v, 16); }
-static inline uint32_t ldg_cg_u32(const void* p) { return ldg_u32(p); }
+static inline uint64_t l2_policy_keep() { return 0; }
+static inline uint64_t l2_policy_stream() { return 0; }
+static inline uint32_t ldg_nc_hint_u32(const void* p, uint64_t) { return ldg_u32(p); }
+static inline void stg_hint_u8(uint8_t* p, uint32_t v, uint64_t) { *p = (uint8_t)v; }
 static inline void tie(uint32_t&, uint32_t) {}
 struct smem_ref { uint8_t* p; };
 static inline smem_ref smem_ref_of(const void* p) { return smem_ref{(uint8_t*)p}; }

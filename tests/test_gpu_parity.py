@@ -45,7 +45,7 @@ def test_encode_fast_byte_identical(ctx):
 
 @pytest.mark.parametrize("variant", [1, 11, 12, 2])
 def test_encode_fast_kernel_variants(ctx, variant):
-    """Every form of the round (always-exact votes / resolved through the table, candidate probes through L1 / L2 only)
+    """Every form of the round (always-exact votes / resolved through the table, plain loads / L2 residency hints)
     emits the same bytes: lz4net's.  Also with fewer encoder warps per SM and the prefetch off."""
     blocks = _inputs(lens=[65536, 65546, 4097, 13, 70000])
     ctx.set_option("encode_variant", variant)
