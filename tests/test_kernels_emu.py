@@ -109,6 +109,25 @@ def test_encode_heuristics_never_change_the_bytes(tune):
     _enc_check(blocks, sched_seed=7, tune=tune)
 
 
+def test_encode_fuzz_small_blocks():
+    """Random content model, length, capacity, buffer alignment, lane schedule, round variant and heuristics: the
+    encoder's return value and bytes are the oracle's, and it never writes outside [dst, dst + cap)."""
+    rng = np.random.default_rng(2024)
+    for trial in range(40):
+        blocks, caps = [], []
+        for _ in range(8):
+            n = int(rng.choice([int(rng.integers(0, 64)), int(rng.integers(64, 3000)), int(rng.integers(3000, 9000))]))
+            d = cases.content(str(rng.choice(cases.MODELS)), n, seed=int(rng.integers(1 << 30))).tobytes()
+            r, _ = oracle.encode(d)
+            cap = int(rng.choice([n + n // 255 + 16, r, max(r - 1, 0), n, int(rng.integers(0, max(r, 1) + 8))]))
+            blocks.append(d); caps.append(cap)
+        tune = (int(rng.choice([0, 12, 64])), int(rng.choice([0, 8, 1000])), int(rng.choice([0, 24, 1000])))
+        res, outs = emu.encode(blocks, caps, sched_seed=int(rng.integers(1, 1 << 20)), src_skew=int(rng.integers(0, 8)),
+                               dst_skew=int(rng.integers(0, 16)), variant=int(rng.choice([1, 2])), tune=tune)
+        for b, c, r, o in zip(blocks, caps, res, outs):
+            assert (r, o) == oracle.encode(b, cap=c), (trial, len(b), c, tune)
+
+
 def test_encode_schedule_independent():
     """Lanes are scheduled in different orders: the result may not depend on lock-step luck."""
     blocks = [cases.content("lowent", 20000, seed=1).tobytes(), cases.content("mixed", 20000, seed=2).tobytes()]
