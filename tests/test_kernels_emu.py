@@ -221,3 +221,28 @@ def test_decode_long_overlapping_matches():
     for lanes in (32, 16, 8, 4, 132, 116, 108, 104):
         res, outs = emu.decode(comp, [len(d) for d in raws], lanes=lanes, known=True, sched_seed=lanes)
         assert outs == raws
+
+
+# ---- LZ4HC (one thread per block: the device source compiled as plain scalar code) ------------------------------------
+@pytest.mark.parametrize("model", cases.MODELS)
+def test_encode_hc_matches_oracle(model):
+    """Byte-identical to the reference's LZ4_compressHC_limitedOutput (original/lz4hc.c:745-755) through the oracle."""
+    for i, n in enumerate([65536, 0, 1, 12, 13, 64, 4097] + cases.random_lengths(3, 65546, seed=5)):
+        d = cases.content(model, n, seed=500 + i).tobytes()
+        assert emu.encode_hc(d) == oracle.encode_hc(d), (model, n)
+
+
+def test_encode_hc_limited_output_and_alignment():
+    for i, m in enumerate(("ETEXT", "lowent", "E50", "periodic")):
+        d = cases.content(m, 5000, seed=40 + i).tobytes()
+        r, _ = oracle.encode_hc(d)
+        for cap in (r, r - 1, len(d), r // 2, 0, 1, 7, 13):
+            assert emu.encode_hc(d, cap=cap) == oracle.encode_hc(d, cap=cap), (m, cap)
+        for skew in (1, 2, 3):
+            assert emu.encode_hc(d, src_skew=skew) == oracle.encode_hc(d), (m, skew)
+
+
+def test_encode_hc_above_64k():
+    for m, n in (("ETEXT", 70001), ("periodic", 140000), ("E100", 200000), ("mixed", 131072)):
+        d = cases.content(m, n, seed=9).tobytes()
+        assert emu.encode_hc(d) == oracle.encode_hc(d), (m, n)
