@@ -6,45 +6,67 @@
 namespace lz4b200 {
 
 // ---- fast encoder: one warp per block, persistent, dynamic block hand-out --------------------------------------------
-// All encoder warps of an SM live in ONE CTA (up to 14 warps x 16 KiB of position tables = 224 KiB of dynamic shared
-// memory): separate CTAs would each pay 1 KiB of system-reserved shared memory, which costs the 14th warp.  The warps
-// never synchronise with each other.  (The launch bound only tells ptxas how many registers it may use: 65536 / 448.)
-constexpr int ENC_MAX_WARPS = 14;
+// All encoder warps of an SM live in ONE CTA.  Up to 14 of them keep their 16 KiB position table in shared memory (14 x
+// 16 KiB = 224 KiB of dynamic shared memory; separate CTAs would each pay 1 KiB of system-reserved shared memory, which
+// costs the 14th warp).  The kernel is a per-warp latency chain (throughput is linear in resident warps), so the warps
+// beyond those 14 -- as many as the register file holds at the launch bound NW -- run the same parse with their table
+// in a global-memory arena that stays L2-resident (16 KiB per warp): a table round trip costs them an L2 round trip,
+// but every one of them is one more block in flight.  The warps never synchronise with each other.
+constexpr int ENC_SMEM_WARPS = 14;
 
-template <int DUP, int LDP>
-__global__ void __launch_bounds__(32 * ENC_MAX_WARPS, 1)
-lz4_encode_fast_kernel(BatchArgs a, uint32_t* counter, EncTune tune)
+template <int DUP, int NW, int GDUP>
+__global__ void __launch_bounds__(32 * NW, 1)
+lz4_encode_fast_kernel(BatchArgs a, uint32_t* counter, EncTune tune, int smem_warps, uint8_t* arena)
 {
     extern __shared__ __align__(16) uint8_t smem[];
-    EncShared* sh = (EncShared*)smem + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool gt = NW > ENC_SMEM_WARPS && warp >= smem_warps;
+    void* table = gt ? (void*)(arena + ((size_t)blockIdx.x * NW + warp) * sizeof(EncShared))
+                     : (void*)((EncShared*)smem + warp);
     for (;;) {
         uint32_t b = 0;
         if (lane == 0) b = atomicAdd(counter, 1u);
         b = simt::shfl(0xFFFFFFFFu, b, 0);
         if (b >= (uint32_t)a.n_blocks) break;
-        const int r = encode_block<DUP, LDP>(sh, a.src + a.src_off[b], a.src_len[b], a.dst + a.dst_off[b], a.dst_cap[b], lane, tune);
+        int r;
+        if (NW > ENC_SMEM_WARPS && gt)
+            r = encode_block<GDUP, 0, true>(table, a.src + a.src_off[b], a.src_len[b], a.dst + a.dst_off[b], a.dst_cap[b], lane, tune);
+        else
+            r = encode_block<DUP, 0, false>(table, a.src + a.src_off[b], a.src_len[b], a.dst + a.dst_off[b], a.dst_cap[b], lane, tune);
         if (lane == 0) a.out_len[b] = r;
     }
 }
 
-template <int DUP, int LDP>
-static cudaError_t launch_fast_t(const BatchArgs& a, uint32_t* counter, int dyn, long long grid, int warps, const EncTune& tune, cudaStream_t stream)
+template <int DUP, int NW, int GDUP>
+static cudaError_t launch_fast_t(const BatchArgs& a, uint32_t* counter, int dyn, long long grid, int warps, int smem_warps,
+                                 uint8_t* arena, const EncTune& tune, cudaStream_t stream)
 {
-    cudaError_t e = cudaFuncSetAttribute(lz4_encode_fast_kernel<DUP, LDP>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+    cudaError_t e = cudaFuncSetAttribute(lz4_encode_fast_kernel<DUP, NW, GDUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
     if (e != cudaSuccess) return e;
-    lz4_encode_fast_kernel<DUP, LDP><<<(unsigned)grid, 32 * warps, dyn, stream>>>(a, counter, tune);
+    lz4_encode_fast_kernel<DUP, NW, GDUP><<<(unsigned)grid, 32 * warps, dyn, stream>>>(a, counter, tune, smem_warps, arena);
     return cudaGetLastError();
 }
 
-cudaError_t launch_encode_fast(const BatchArgs& a, uint32_t* counter, int warps_per_sm, const int* tune4, int variant,
-                               const DeviceInfo& dev, cudaStream_t stream, int64_t* launches)
+size_t encode_arena_bytes(int warps_per_sm, const DeviceInfo& dev)
+{
+    return warps_per_sm > ENC_SMEM_WARPS ? (size_t)28 * dev.num_sms * sizeof(EncShared) : 0;     // one slot per warp of the widest kernel
+}
+
+cudaError_t launch_encode_fast(const BatchArgs& a, uint32_t* counter, int warps_per_sm, int smem_warps_max, const int* tune4, int variant,
+                               void* arena, const DeviceInfo& dev, cudaStream_t stream, int64_t* launches)
 {
     if (a.n_blocks <= 0) return cudaSuccess;
-    int max_warps = dev.smem_optin / (int)sizeof(EncShared);
-    if (max_warps > ENC_MAX_WARPS) max_warps = ENC_MAX_WARPS;
-    if (max_warps < 1) max_warps = 1;
-    if (warps_per_sm < 1 || warps_per_sm > max_warps) warps_per_sm = max_warps;
+    int smem_warps = dev.smem_optin / (int)sizeof(EncShared);
+    if (smem_warps > ENC_SMEM_WARPS) smem_warps = ENC_SMEM_WARPS;
+    if (smem_warps < 1) smem_warps = 1;
+    if (warps_per_sm < 1) warps_per_sm = smem_warps;
+    const int smem_full = smem_warps;
+    if (warps_per_sm > ENC_SMEM_WARPS && smem_warps_max > 0 && smem_warps_max < smem_warps) smem_warps = smem_warps_max;   // (tests: global-table warps in small batches)
+    // the launch bounds the kernel is built for: 14 (all tables in shared memory), 18, 20, 24, 28
+    const int nw = warps_per_sm <= 14 ? 14 : (warps_per_sm <= 18 ? 18 : (warps_per_sm <= 20 ? 20 : (warps_per_sm <= 24 ? 24 : 28)));
+    if (warps_per_sm > nw) warps_per_sm = nw;
+    if (nw == 14 && warps_per_sm > smem_warps) warps_per_sm = smem_warps;
+    if (nw > 14 && (smem_full < ENC_SMEM_WARPS || !arena)) return cudaErrorInvalidValue;
     // small batches: spread the blocks over the SMs first
     long long grid = dev.num_sms;
     int warps = warps_per_sm;
@@ -52,18 +74,26 @@ cudaError_t launch_encode_fast(const BatchArgs& a, uint32_t* counter, int warps_
         warps = (int)((a.n_blocks + dev.num_sms - 1) / dev.num_sms);
         grid = (a.n_blocks + warps - 1) / warps;
     }
-    const int dyn = warps * (int)sizeof(EncShared);
+    const int sw = warps < smem_warps ? warps : smem_warps;
+    const int dyn = sw * (int)sizeof(EncShared);
     cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), stream);
     if (e != cudaSuccess) return e;
     if (launches) ++*launches;
     EncTune tune; tune.pf_dist = tune4[0]; tune.lane_copy_max = tune4[1]; tune.probe_max = tune4[2]; tune.wide_min = tune4[3];
-    switch (variant) {                      // variant % 10: how same-hash iterations of one round are found (lz4_encode.cuh);
-                                            // variant / 10: plain read-only loads (0) or L2 residency hints (1: input evict-last, output evict-first)
-    case 1:  return launch_fast_t<1, 0>(a, counter, dyn, grid, warps, tune, stream);  // always exact: one vote per hash bit
-    case 11: return launch_fast_t<1, 1>(a, counter, dyn, grid, warps, tune, stream);
-    case 12: return launch_fast_t<2, 1>(a, counter, dyn, grid, warps, tune, stream);
-    default: return launch_fast_t<2, 0>(a, counter, dyn, grid, warps, tune, stream);  // through the table, pairs resolved in place
+    uint8_t* ar = (uint8_t*)arena;
+    // variant % 10: how same-hash iterations of one round are found by the shared-memory warps (lz4_encode.cuh): 1 = always
+    // exact (one vote per hash bit), 2 = through the table, pairs resolved in place; variant / 10 (0 -> 2): the same for
+    // the warps whose table is in global memory
+#define LZ4B200_ENC_CASE(NW_) \
+    case NW_: return variant / 10 == 1 ? launch_fast_t<2, NW_, 1>(a, counter, dyn, grid, warps, sw, ar, tune, stream) \
+                                       : launch_fast_t<2, NW_, 2>(a, counter, dyn, grid, warps, sw, ar, tune, stream);
+    switch (nw) {
+    LZ4B200_ENC_CASE(18) LZ4B200_ENC_CASE(20) LZ4B200_ENC_CASE(24) LZ4B200_ENC_CASE(28)
+    default: break;
     }
+#undef LZ4B200_ENC_CASE
+    return variant % 10 == 1 ? launch_fast_t<1, 14, 1>(a, counter, dyn, grid, warps, sw, ar, tune, stream)
+                             : launch_fast_t<2, 14, 2>(a, counter, dyn, grid, warps, sw, ar, tune, stream);
 }
 
 // ---- HC encoder: one THREAD per block, state arena in global memory -------------------------------------------------

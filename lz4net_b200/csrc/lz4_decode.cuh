@@ -166,6 +166,9 @@ SIMT_DEV int decode_careful(DecStream<G>& st, DecCursor& cur, int isize, uint8_t
         else       { while (ip < isize && s == 255 && L <= LEN_LIMIT) { s = st.byte_at(ip++); L += (int)s; } }
         if (L < 0 || L > LEN_LIMIT) { *result = -ip - 1; return -1; }
     }
+    // a run longer than the rest of either buffer fails every end test below; rejecting it here keeps op + L and ip + L
+    // inside int for blocks of any size
+    if (L > isize - ip || L > cap - op) { *result = -ip - 1; return -1; }
     int end = op + L;
     bool last;
     if (KNOWN) last = end > cap - 8;                               // :847
@@ -192,6 +195,7 @@ SIMT_DEV int decode_careful(DecStream<G>& st, DecCursor& cur, int isize, uint8_t
         else       { while (ip < isize - 6 && M <= LEN_LIMIT) { s = st.byte_at(ip++); M += (int)s; if (s != 255) break; } }
         if (M < 0 || M > LEN_LIMIT) { *result = -ip - 1; return -1; }
     }
+    if (M > cap - op) { *result = -ip - 1; return -1; }            // (keeps op + M + 4 inside int; fails :893 / :1025 anyway)
     end = op + M + 4;
     if (end > cap - 5) { *result = -ip - 1; return -1; }           // :893 / :1025 -- the last 5 bytes are literals
     simt::syncwarp(st.gmask);                                      // literal (and earlier match) stores -> match loads
@@ -382,11 +386,9 @@ SIMT_DEV int decode_block_staged(DecStream<G>& st, DecStage<G>* stage, const uin
     const int out_fast = cap - (FAST_L + FAST_M + 16);
     int in_fast = st.window(0, isize) - DEC_AHEAD;
     for (;;) {
-        // Slide the input window when this group needs it -- or when a group running in lock step with it slides anyway
-        // (same argument as for the flushes below: a refill executed by one group alone costs the warp as much as one
-        // executed by all).  Everybody then looks one chunk further ahead, so the groups stay together for a while.
-        if (simt::ballot(simt::converged(gmask), cur.ip > in_fast))
-            in_fast = st.window(cur.ip, isize, DecGeom<G>::CHUNK) - DEC_AHEAD;
+        // Slide the input window when this group needs it (one chunk further ahead than strictly needed, so that it
+        // happens about once per chunk).  The decision is the group's own: a vote over exactly the group's lanes.
+        if (cur.ip > in_fast) in_fast = st.window(cur.ip, isize, DecGeom<G>::CHUNK) - DEC_AHEAD;
         if (cur.ip <= in_fast && cur.op <= out_fast) {
             const uint8_t* const h = rb + (((uint32_t)cur.ip + rot) & (RING - 1));
             // branch-free header parse: both possible length bytes are loaded unconditionally (they are inside the
@@ -442,12 +444,9 @@ SIMT_DEV int decode_block_staged(DecStream<G>& st, DecStage<G>* stage, const uin
                     }
                     ohi += (int)(L + M);
                     cur.ip += (int)adv; cur.op = (int)(opl + M);
-                    // Flush when this group's stage is full -- or when a group that runs in lock step with this one
-                    // flushes anyway: the groups of a warp share every instruction, so a flush executed by one group
-                    // alone costs the warp as much as one executed by all of them (measured: 24 % of the instructions
-                    // of the E50 decode were flushes of single groups).  Flushing early is always valid.
-                    const uint32_t cm = simt::converged(gmask);
-                    if (simt::ballot(cm, ohi > FLUSH_AT)) flush(false);
+                    // Flush when this group's stage is full (group-uniform state: every lane of the group takes the same
+                    // branch, and the collectives inside flush() name exactly the group's lanes).
+                    if (ohi > FLUSH_AT) flush(false);
                     continue;
                 }
             }

@@ -23,9 +23,6 @@ SIMT_DEV uint32_t ballot(uint32_t mask, bool p) { return __ballot_sync(mask, p);
 SIMT_DEV uint32_t match_any(uint32_t mask, uint32_t v) { return __match_any_sync(mask, v); }
 SIMT_DEV uint32_t reduce_max(uint32_t mask, uint32_t v) { return __reduce_max_sync(mask, v); }     // REDUX
 SIMT_DEV void syncwarp(uint32_t mask) { __syncwarp(mask); }
-// Lanes of the warp that are executing this instruction together right now (a superset of the caller's own group
-// `own`).  For opportunistic co-scheduling of work that is valid at any time for every group (never for correctness).
-SIMT_DEV uint32_t converged(uint32_t own) { return __activemask() | own; }
 SIMT_DEV int ffs(uint32_t v) { return __ffs((int)v); }
 SIMT_DEV int clz(uint32_t v) { return __clz((int)v); }
 SIMT_DEV int popc(uint32_t v) { return __popc(v); }
@@ -69,6 +66,13 @@ SIMT_DEV uint32_t lds_u16(smem_ref r, uint32_t off) { uint16_t v; asm volatile("
 SIMT_DEV uint32_t lds_u32(smem_ref r, uint32_t off) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(r.a + off) : "memory"); return v; }
 SIMT_DEV void sts_u16(smem_ref r, uint32_t off, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" :: "r"(r.a + off), "h"((uint16_t)v) : "memory"); }
 SIMT_DEV void sts_u32(smem_ref r, uint32_t off, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(r.a + off), "r"(v) : "memory"); }
+
+// position-table entries kept in global memory (encoder warps beyond the ones shared memory holds): written and read
+// back by different lanes of one warp with a __syncwarp() between -- volatile asm so the compiler keeps every access.
+SIMT_DEV uint32_t ldt_u16(const void* p) { uint16_t v; asm volatile("ld.global.u16 %0, [%1];" : "=h"(v) : "l"(p) : "memory"); return v; }
+SIMT_DEV uint32_t ldt_u32(const void* p) { uint32_t v; asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+SIMT_DEV void stt_u16(void* p, uint32_t v) { asm volatile("st.global.u16 [%0], %1;" :: "l"(p), "h"((uint16_t)v) : "memory"); }
+SIMT_DEV void stt_u32(void* p, uint32_t v) { asm volatile("st.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
 
 // software prefetch of the line holding *p (no destination register, never faults the warp's progress)
 SIMT_DEV void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }

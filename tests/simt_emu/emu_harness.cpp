@@ -59,6 +59,7 @@ void dec_entry(int lane, void* arg)
 }
 
 int g_enc_variant = 2;
+int g_enc_gt = 0;            // 1: the position table is addressed as global memory (the warps beyond the 14 shared-memory ones)
 EncTune g_enc_tune;
 
 struct EncJob {
@@ -70,8 +71,11 @@ void enc_entry(int lane, void* arg)
 {
     EncJob* j = (EncJob*)arg;
     for (int b = 0; b < j->nblocks; b++) {
-        int r = g_enc_variant == 1 ? encode_block<1>(j->sh, j->src[b], j->n[b], j->dst[b], j->cap[b], lane, g_enc_tune)
-                                   : encode_block<2>(j->sh, j->src[b], j->n[b], j->dst[b], j->cap[b], lane, g_enc_tune);
+        int r;
+        if (g_enc_gt) r = g_enc_variant == 1 ? encode_block<1, 0, true>(j->sh, j->src[b], j->n[b], j->dst[b], j->cap[b], lane, g_enc_tune)
+                                             : encode_block<2, 0, true>(j->sh, j->src[b], j->n[b], j->dst[b], j->cap[b], lane, g_enc_tune);
+        else          r = g_enc_variant == 1 ? encode_block<1>(j->sh, j->src[b], j->n[b], j->dst[b], j->cap[b], lane, g_enc_tune)
+                                             : encode_block<2>(j->sh, j->src[b], j->n[b], j->dst[b], j->cap[b], lane, g_enc_tune);
         if (lane == 0) j->result[b] = r;
     }
 }
@@ -100,7 +104,7 @@ int emu_encode_hc(const uint8_t* src, int n, uint8_t* dst, int cap)
     return r;
 }
 
-void emu_set_encode_variant(int v) { g_enc_variant = v; }
+void emu_set_encode_variant(int v) { g_enc_variant = v % 10; g_enc_gt = v >= 10; }
 void emu_set_encode_tune(int lane_copy_max, int probe_max, int wide_min)
 {
     g_enc_tune.lane_copy_max = lane_copy_max; g_enc_tune.probe_max = probe_max; g_enc_tune.wide_min = wide_min;

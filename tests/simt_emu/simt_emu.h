@@ -29,7 +29,6 @@ static inline uint32_t shfl(uint32_t mask, uint32_t v, int src) { return simt_em
 static inline uint32_t ballot(uint32_t mask, bool p) { return simt_emu::collective(simt_emu::OP_BALLOT, mask, p ? 1u : 0u, 0); }
 static inline uint32_t match_any(uint32_t mask, uint32_t v) { return simt_emu::collective(simt_emu::OP_MATCH, mask, v, 0); }
 static inline uint32_t reduce_max(uint32_t mask, uint32_t v) { return simt_emu::collective(simt_emu::OP_RMAX, mask, v, 0); }
-static inline uint32_t converged(uint32_t own) { return own; }     // the emulator's lanes are never known to be converged beyond their group
 static inline void syncwarp(uint32_t mask) { simt_emu::collective(simt_emu::OP_SYNC, mask, 0, 0); }
 static inline int ffs(uint32_t v) { return __builtin_ffs((int)v); }
 static inline int clz(uint32_t v) { return v ? __builtin_clz(v) : 32; }
@@ -58,6 +57,10 @@ static inline uint32_t lds_u16(smem_ref r, uint32_t off) { uint16_t v; memcpy(&v
 static inline uint32_t lds_u32(smem_ref r, uint32_t off) { uint32_t v; memcpy(&v, r.p + off, 4); return v; }
 static inline void sts_u16(smem_ref r, uint32_t off, uint32_t v) { uint16_t t = (uint16_t)v; memcpy(r.p + off, &t, 2); }
 static inline void sts_u32(smem_ref r, uint32_t off, uint32_t v) { memcpy(r.p + off, &v, 4); }
+static inline uint32_t ldt_u16(const void* p) { uint16_t v; memcpy(&v, p, 2); return v; }
+static inline uint32_t ldt_u32(const void* p) { uint32_t v; memcpy(&v, p, 4); return v; }
+static inline void stt_u16(void* p, uint32_t v) { uint16_t t = (uint16_t)v; memcpy(p, &t, 2); }
+static inline void stt_u32(void* p, uint32_t v) { memcpy(p, &v, 4); }
 static inline void prefetch_l1(const void*) {}
 static inline void prefetch_l2(const void*) {}
 

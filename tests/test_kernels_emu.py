@@ -94,7 +94,7 @@ def test_encode_unaligned_buffers(skew):
         assert (r, o) == oracle.encode(b)
 
 
-@pytest.mark.parametrize("variant", [1])
+@pytest.mark.parametrize("variant", [1, 11, 12])
 def test_encode_other_duplicate_detectors(variant):
     """The always-exact (vote-per-hash-bit, 32 iterations per round) form of the round gives the same bytes as the default."""
     blocks = [cases.content(m, n, seed=90 + i).tobytes() for i, m in enumerate(cases.MODELS) for n in (65536, 4097)]
@@ -123,7 +123,7 @@ def test_encode_fuzz_small_blocks():
             blocks.append(d); caps.append(cap)
         tune = (int(rng.choice([0, 12, 64])), int(rng.choice([0, 8, 1000])), int(rng.choice([0, 24, 1000])))
         res, outs = emu.encode(blocks, caps, sched_seed=int(rng.integers(1, 1 << 20)), src_skew=int(rng.integers(0, 8)),
-                               dst_skew=int(rng.integers(0, 16)), variant=int(rng.choice([1, 2])), tune=tune)
+                               dst_skew=int(rng.integers(0, 16)), variant=int(rng.choice([1, 2, 11, 12])), tune=tune)
         for b, c, r, o in zip(blocks, caps, res, outs):
             assert (r, o) == oracle.encode(b, cap=c), (trial, len(b), c, tune)
 
