@@ -500,7 +500,8 @@ int lz4b200_set_option(lz4b200_ctx* c, const char* key, int64_t value)
     std::string k(key);
     if (k == "decode_lanes") {
         const int64_t g = value % 100;                 // 100 + G = the output-staged variant of the G-lane decoder
-        if ((g != 4 && g != 8 && g != 16 && g != 32) || (value != g && value != 100 + g)) return fail(LZ4B200_E_ARG, "decode_lanes must be 4, 8, 16, 32 (or 100 + that)");
+        const bool lpb = value == 1 || value == 2;     // one lane per block (512- / 256-byte output ring)
+        if (!lpb && ((g != 4 && g != 8 && g != 16 && g != 32) || (value != g && value != 100 + g))) return fail(LZ4B200_E_ARG, "decode_lanes must be 1, 2, 4, 8, 16, 32 (or 100 + one of the last four)");
         c->decode_lanes = (int)value; c->decode_lanes_auto = false;
     }
     else if (k == "decode_lanes_auto") { c->decode_lanes_auto = value != 0; }

@@ -1,6 +1,7 @@
 // decode.cu -- kernel + launcher for the batched decoder (see lz4_decode.cuh for the algorithm).
 #include "kernels.h"
 #include "lz4_decode.cuh"
+#include "lz4_decode_lpb.cuh"
 
 namespace lz4b200 {
 
@@ -67,6 +68,38 @@ static cudaError_t launch_g(const BatchArgs& a, bool known, bool staged, uint32_
     return known ? launch_one<G, true, false>(a, counter, dev, stream) : launch_one<G, false, false>(a, counter, dev, stream);
 }
 
+// ---- lane-per-block decoder (lz4_decode_lpb.cuh): one CTA per SM, as many warps as shared memory holds rings for --------
+constexpr int LPB_MAX_WARPS = 13;
+
+template <bool KNOWN, class GEO>
+__global__ void __launch_bounds__(32 * LPB_MAX_WARPS, 1)
+lz4_decode_lpb_kernel(BatchArgs a, uint32_t* counter)
+{
+    extern __shared__ __align__(128) uint8_t lpb_smem[];
+    LpbShared<GEO>* sh = (LpbShared<GEO>*)lpb_smem + (threadIdx.x >> 5);
+    const LpbBatch b{a.src, a.src_off, a.src_len, a.dst, a.dst_off, a.dst_cap, a.out_len, a.n_blocks};
+    lpb_decode_warp<KNOWN, GEO>(sh, b, counter, (int)(threadIdx.x & 31));
+}
+
+template <bool KNOWN, class GEO>
+static cudaError_t launch_lpb(const BatchArgs& a, uint32_t* counter, const DeviceInfo& dev, cudaStream_t stream)
+{
+    int warps = dev.smem_optin / (int)sizeof(LpbShared<GEO>);
+    if (warps > LPB_MAX_WARPS) warps = LPB_MAX_WARPS;
+    if (warps < 1) return cudaErrorInvalidConfiguration;
+    long long grid = dev.num_sms;
+    const long long want_warps = ((long long)a.n_blocks + 31) / 32;          // one block per lane
+    if (want_warps < grid * warps) {                                         // small batch: spread the warps over the SMs first
+        warps = (int)((want_warps + grid - 1) / grid);
+        grid = (want_warps + warps - 1) / warps;
+    }
+    const int dyn = warps * (int)sizeof(LpbShared<GEO>);
+    cudaError_t e = cudaFuncSetAttribute(lz4_decode_lpb_kernel<KNOWN, GEO>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+    if (e != cudaSuccess) return e;
+    lz4_decode_lpb_kernel<KNOWN, GEO><<<(unsigned)grid, 32 * warps, dyn, stream>>>(a, counter);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_decode(const BatchArgs& a, bool known_len, int lanes, uint32_t* counter,
                           const DeviceInfo& dev, cudaStream_t stream, int64_t* launches)
 {
@@ -76,6 +109,8 @@ cudaError_t launch_decode(const BatchArgs& a, bool known_len, int lanes, uint32_
     if (launches) ++*launches;
     const bool staged = lanes >= 100;            // lanes = 100 + G selects the output-staged variant
     switch (lanes % 100) {
+    case 1:  return known_len ? launch_lpb<true, LpbGeom<256, 512>>(a, counter, dev, stream) : launch_lpb<false, LpbGeom<256, 512>>(a, counter, dev, stream);
+    case 2:  return known_len ? launch_lpb<true, LpbGeom<256, 256>>(a, counter, dev, stream) : launch_lpb<false, LpbGeom<256, 256>>(a, counter, dev, stream);
     case 4:  return launch_g<4>(a, known_len, staged, counter, dev, stream);
     case 8:  return launch_g<8>(a, known_len, staged, counter, dev, stream);
     case 16: return launch_g<16>(a, known_len, staged, counter, dev, stream);

@@ -64,6 +64,9 @@ struct smem_ref { uint32_t a; };
 SIMT_DEV smem_ref smem_ref_of(const void* p) { smem_ref r; r.a = (uint32_t)__cvta_generic_to_shared(p); asm volatile("" : "+r"(r.a)); return r; }
 SIMT_DEV uint32_t lds_u16(smem_ref r, uint32_t off) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(r.a + off) : "memory"); return v; }
 SIMT_DEV uint32_t lds_u32(smem_ref r, uint32_t off) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(r.a + off) : "memory"); return v; }
+SIMT_DEV uint32_t lds_u8(smem_ref r, uint32_t off) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(r.a + off) : "memory"); return v; }
+SIMT_DEV uint4 lds_v4(smem_ref r, uint32_t off) { uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(r.a + off) : "memory"); return v; }
+SIMT_DEV void sts_u8(smem_ref r, uint32_t off, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(r.a + off), "r"(v) : "memory"); }
 SIMT_DEV void sts_u16(smem_ref r, uint32_t off, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" :: "r"(r.a + off), "h"((uint16_t)v) : "memory"); }
 SIMT_DEV void sts_u32(smem_ref r, uint32_t off, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(r.a + off), "r"(v) : "memory"); }
 
@@ -73,6 +76,15 @@ SIMT_DEV uint32_t ldt_u16(const void* p) { uint16_t v; asm volatile("ld.global.u
 SIMT_DEV uint32_t ldt_u32(const void* p) { uint32_t v; asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 SIMT_DEV void stt_u16(void* p, uint32_t v) { asm volatile("st.global.u16 [%0], %1;" :: "l"(p), "h"((uint16_t)v) : "memory"); }
 SIMT_DEV void stt_u32(void* p, uint32_t v) { asm volatile("st.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+
+// Ampere-style asynchronous copy, 16 bytes global -> shared per lane (both addresses 16-byte aligned), tracked per thread:
+// every lane of a warp copies for itself in ONE instruction (the bulk form, UBLKCP, takes uniform operands and would be
+// serialised lane by lane).  commit closes the group of copies issued so far; wait<N> returns when all but the N most
+// recent groups of the calling thread have landed.
+SIMT_DEV void cp_async16(smem_ref r, uint32_t off, const void* g) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(r.a + off), "l"(g) : "memory"); }
+SIMT_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> SIMT_DEV void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+SIMT_DEV uint32_t atomic_inc(uint32_t* p) { return atomicAdd(p, 1u); }
 
 // software prefetch of the line holding *p (no destination register, never faults the warp's progress)
 SIMT_DEV void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }

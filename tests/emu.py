@@ -40,7 +40,7 @@ def _ptr_array(arrs):
     return (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
 
 
-def decode(blocks, caps, lanes=32, known=True, sched_seed=1, src_skew=0):
+def decode(blocks, caps, lanes=32, known=True, sched_seed=1, src_skew=0, dst_skew=0):
     """blocks: list of bytes (compressed); caps: list of int. Returns (results, outputs).  src_skew shifts the
     compressed bytes inside their buffer to exercise unaligned stream starts."""
     n = len(blocks)
@@ -49,18 +49,23 @@ def decode(blocks, caps, lanes=32, known=True, sched_seed=1, src_skew=0):
         a = np.zeros(src_skew + len(b) + 64, np.uint8)
         a[src_skew:src_skew + len(b)] = np.frombuffer(b, np.uint8)
         srcs.append(a)
-    dsts = [np.full(max(c, 0) + 96, 0xCD, np.uint8) for c in caps]
+    dsts = [np.full(max(c, 0) + 96 + dst_skew, 0xCD, np.uint8) for c in caps]
     isz = np.array([len(b) for b in blocks], np.int32)
     cps = np.array(caps, np.int32)
     res = np.zeros(n, np.int32)
     sp = (C.c_void_p * n)(*[a.ctypes.data + src_skew for a in srcs])
-    dp = (C.c_void_p * n)(*[a.ctypes.data + 32 for a in dsts])       # 32-byte red zone in front
-    lib().emu_decode(lanes, int(known), n, sp, isz.ctypes.data_as(C.c_void_p), dp, cps.ctypes.data_as(C.c_void_p),
-                     res.ctypes.data_as(C.c_void_p), C.c_uint64(sched_seed))
+    dp = (C.c_void_p * n)(*[a.ctypes.data + 32 + dst_skew for a in dsts])       # 32-byte red zone in front
+    if lanes in (1, 2):      # lane-per-block decoder (1: 512-byte output ring, 2: 256-byte)
+        lib().emu_decode_lpb(lanes - 1, int(known), n, sp, isz.ctypes.data_as(C.c_void_p), dp, cps.ctypes.data_as(C.c_void_p),
+                             res.ctypes.data_as(C.c_void_p), C.c_uint64(sched_seed))
+    else:
+        lib().emu_decode(lanes, int(known), n, sp, isz.ctypes.data_as(C.c_void_p), dp, cps.ctypes.data_as(C.c_void_p),
+                         res.ctypes.data_as(C.c_void_p), C.c_uint64(sched_seed))
     outs = []
+    lo = 32 + dst_skew
     for d, c in zip(dsts, caps):
-        assert (d[:32] == 0xCD).all() and (d[32 + max(c, 0):] == 0xCD).all(), "decoder wrote outside [dst, dst+cap)"
-        outs.append(d[32:32 + max(c, 0)].tobytes())
+        assert (d[:lo] == 0xCD).all() and (d[lo + max(c, 0):] == 0xCD).all(), "decoder wrote outside [dst, dst+cap)"
+        outs.append(d[lo:lo + max(c, 0)].tobytes())
     return res.tolist(), outs
 
 

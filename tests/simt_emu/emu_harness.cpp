@@ -3,6 +3,7 @@
 #define LZ4B200_SIMT_EMU 1
 #include "simt_emu.h"
 #include "lz4_decode.cuh"
+#include "lz4_decode_lpb.cuh"
 #include "lz4_encode.cuh"
 #include "lz4hc_encode.cuh"
 #include <stdlib.h>
@@ -58,6 +59,20 @@ void dec_entry(int lane, void* arg)
     }
 }
 
+// lane-per-block decoder: the whole warp loop of the kernel, blocks handed out through the counter
+struct LpbJob { LpbBatch a; uint32_t counter; int known; int geo; void* sh; };
+void lpb_entry(int lane, void* arg)
+{
+    LpbJob* j = (LpbJob*)arg;
+    if (j->geo == 1) {
+        typedef LpbGeom<256, 256> G;
+        j->known ? lpb_decode_warp<true, G>((LpbShared<G>*)j->sh, j->a, &j->counter, lane) : lpb_decode_warp<false, G>((LpbShared<G>*)j->sh, j->a, &j->counter, lane);
+    } else {
+        typedef LpbGeom<256, 512> G;
+        j->known ? lpb_decode_warp<true, G>((LpbShared<G>*)j->sh, j->a, &j->counter, lane) : lpb_decode_warp<false, G>((LpbShared<G>*)j->sh, j->a, &j->counter, lane);
+    }
+}
+
 int g_enc_variant = 2;
 int g_enc_gt = 0;            // 1: the position table is addressed as global memory (the warps beyond the 14 shared-memory ones)
 EncTune g_enc_tune;
@@ -92,6 +107,21 @@ void emu_decode(int G, int known, int nblocks, const uint8_t* const* src, const 
     j->G = G; j->known = known != 0; j->nblocks = nblocks; j->src = src; j->isize = isize; j->dst = dst; j->cap = cap; j->result = result;
     simt_emu::run_warp(dec_entry, j, sched_seed);
     delete j;
+}
+
+void emu_decode_lpb(int geo, int known, int nblocks, const uint8_t* const* src, const int* isize,
+                    uint8_t* const* dst, const int* cap, int* result, uint64_t sched_seed)
+{
+    std::vector<int64_t> so(nblocks), dof(nblocks);
+    const uint8_t* sb = nblocks ? src[0] : nullptr; uint8_t* db = nblocks ? dst[0] : nullptr;
+    for (int i = 0; i < nblocks; i++) { so[i] = src[i] - sb; dof[i] = dst[i] - db; }
+    LpbJob j;
+    j.a = LpbBatch{sb, so.data(), isize, db, dof.data(), cap, result, nblocks};
+    j.counter = 0; j.known = known; j.geo = geo;
+    j.sh = aligned_alloc(128, sizeof(LpbShared<LpbGeom<256, 512>>));
+    memset(j.sh, 0xA5, sizeof(LpbShared<LpbGeom<256, 512>>));
+    simt_emu::run_warp(lpb_entry, &j, sched_seed);
+    free(j.sh);
 }
 
 // the HC encoder is one thread per block: plain scalar code, no warp needed

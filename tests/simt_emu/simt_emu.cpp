@@ -3,6 +3,8 @@
 #include <ucontext.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <vector>
+#include <deque>
 
 namespace simt_emu {
 
@@ -99,6 +101,23 @@ void run_warp(void (*fn)(int, void*), void* arg, uint64_t seed)
             fprintf(stderr, " (done flags)\n");
             abort();
         }
+    }
+}
+}
+
+// ---- deferred cp.async (per lane) -------------------------------------------------------------------------------
+namespace simt {
+struct PendingCopy { void* dst; const void* src; };
+static std::deque<std::vector<PendingCopy>> g_groups[32];
+static std::vector<PendingCopy> g_open[32];
+void cp_async16_emu(void* sdst, const void* gsrc) { g_open[simt_emu::current_lane()].push_back(PendingCopy{sdst, gsrc}); }
+void cp_async_commit_emu() { int l = simt_emu::current_lane(); g_groups[l].push_back(g_open[l]); g_open[l].clear(); }
+void cp_async_wait_emu(int n)
+{
+    int l = simt_emu::current_lane();
+    while ((int)g_groups[l].size() > n) {
+        for (const PendingCopy& c : g_groups[l].front()) memcpy(c.dst, c.src, 16);
+        g_groups[l].pop_front();
     }
 }
 }

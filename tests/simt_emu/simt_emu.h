@@ -55,12 +55,24 @@ struct smem_ref { uint8_t* p; };
 static inline smem_ref smem_ref_of(const void* p) { return smem_ref{(uint8_t*)p}; }
 static inline uint32_t lds_u16(smem_ref r, uint32_t off) { uint16_t v; memcpy(&v, r.p + off, 2); return v; }
 static inline uint32_t lds_u32(smem_ref r, uint32_t off) { uint32_t v; memcpy(&v, r.p + off, 4); return v; }
+static inline uint32_t lds_u8(smem_ref r, uint32_t off) { return r.p[off]; }
+static inline uint4 lds_v4(smem_ref r, uint32_t off) { uint4 v; memcpy(&v, r.p + off, 16); return v; }
+static inline void sts_u8(smem_ref r, uint32_t off, uint32_t v) { r.p[off] = (uint8_t)v; }
 static inline void sts_u16(smem_ref r, uint32_t off, uint32_t v) { uint16_t t = (uint16_t)v; memcpy(r.p + off, &t, 2); }
 static inline void sts_u32(smem_ref r, uint32_t off, uint32_t v) { memcpy(r.p + off, &v, 4); }
 static inline uint32_t ldt_u16(const void* p) { uint16_t v; memcpy(&v, p, 2); return v; }
 static inline uint32_t ldt_u32(const void* p) { uint32_t v; memcpy(&v, p, 4); return v; }
 static inline void stt_u16(void* p, uint32_t v) { uint16_t t = (uint16_t)v; memcpy(p, &t, 2); }
 static inline void stt_u32(void* p, uint32_t v) { memcpy(p, &v, 4); }
+// cp.async: the copy is DEFERRED until the wait that covers its group (per lane), so that code which reads a unit before
+// waiting for it, or overwrites a ring slot that is still to be read, fails in the emulator as well
+void cp_async16_emu(void* sdst, const void* gsrc);
+void cp_async_commit_emu();
+void cp_async_wait_emu(int n);
+static inline void cp_async16(smem_ref r, uint32_t off, const void* g) { cp_async16_emu(r.p + off, g); }
+static inline void cp_async_commit() { cp_async_commit_emu(); }
+template <int N> static inline void cp_async_wait() { cp_async_wait_emu(N); }
+static inline uint32_t atomic_inc(uint32_t* p) { return (*p)++; }
 static inline void prefetch_l1(const void*) {}
 static inline void prefetch_l2(const void*) {}
 

@@ -120,7 +120,7 @@ def test_golden_vectors(ctx):
             assert r2 == c[mode]["len_cap_n"], (c["name"], mode)
 
 
-@pytest.mark.parametrize("lanes", [32, 16, 8, 4, 132, 116, 108, 104])
+@pytest.mark.parametrize("lanes", [32, 16, 8, 4, 132, 116, 108, 104, 1, 2])
 @pytest.mark.parametrize("known", [True, False])
 def test_decode_bit_exact(ctx, lanes, known):
     ctx.set_option("decode_lanes", lanes)
@@ -156,8 +156,10 @@ def test_decode_size_invariants(ctx):
         assert any(e < 0 for e in expect) and any(e >= 0 for e in expect)
 
 
+@pytest.mark.parametrize("lanes", [16, 1])
 @pytest.mark.parametrize("known", [True, False])
-def test_decode_corrupt_streams(ctx, known):
+def test_decode_corrupt_streams(ctx, known, lanes):
+    ctx.set_option("decode_lanes", lanes)
     rng = np.random.default_rng(5)
     comp, caps = [], []
     for i in range(400):
@@ -173,6 +175,7 @@ def test_decode_corrupt_streams(ctx, known):
             c[int(rng.integers(0, len(c)))] = 0xFF
         comp.append(bytes(c)); caps.append(len(d))
     res, outs = ctx.decode_blocks(comp, caps, known=known)
+    ctx.set_option("decode_lanes_auto", 1)
     for c, cap, r, o in zip(comp, caps, res, outs):
         er, eo = (oracle.decode_known if known else oracle.decode_unknown)(c, cap)
         assert (r < 0) == (er < 0), (r, er)
@@ -462,7 +465,7 @@ def test_large_batch_properties(ctx, cls):
     out = torch.empty(nb * bs, dtype=torch.uint8, device="cuda")
     used = torch.zeros(nb, dtype=torch.int32, device="cuda")
     try:
-        for lanes in (32, 16, 108, 104):
+        for lanes in (32, 16, 108, 104, 1, 2):
             ctx.set_option("decode_lanes", lanes)
             out.zero_()
             batch.decode(ctx, slots, do, clen, out, so, sl, used, known=True)

@@ -135,7 +135,7 @@ def test_encode_schedule_independent():
         _enc_check(blocks, sched_seed=seed)
 
 
-@pytest.mark.parametrize("lanes", [32, 16, 8, 4, 132, 116, 108, 104])
+@pytest.mark.parametrize("lanes", [32, 16, 8, 4, 132, 116, 108, 104, 1, 2])
 @pytest.mark.parametrize("known", [True, False])
 def test_decode_matches_oracle(lanes, known):
     blocks, raws = [], []
@@ -150,7 +150,7 @@ def test_decode_matches_oracle(lanes, known):
         assert o == d
 
 
-@pytest.mark.parametrize("lanes", [32, 8, 116])
+@pytest.mark.parametrize("lanes", [32, 8, 116, 1, 2])
 def test_decode_size_invariants(lanes):
     """fuzzer.c:176-210 -- exact size works; size +-1 fails; verdicts equal the oracle's (which is pinned to the reference)."""
     from lz4net_b200 import synth
@@ -191,9 +191,10 @@ def test_decode_corrupt_streams_never_escape(known):
             c[int(rng.integers(0, len(c)))] = 0xFF
         comp.append(bytes(c)); caps.append(len(d))
     res, outs = emu.decode(comp, caps, lanes=32, known=known, sched_seed=13)
-    res2, outs2 = emu.decode(comp, caps, lanes=108, known=known, sched_seed=14)       # output-staged variant, 8 lanes
-    assert [r < 0 for r in res2] == [r < 0 for r in res] and [r for r in res2 if r >= 0] == [r for r in res if r >= 0]
-    assert [o for r, o in zip(res2, outs2) if r >= 0] == [o for r, o in zip(res, outs) if r >= 0]
+    for other in (108, 1, 2):                                   # output-staged variant with 8 lanes; lane-per-block decoder
+        res2, outs2 = emu.decode(comp, caps, lanes=other, known=known, sched_seed=14)
+        assert [r < 0 for r in res2] == [r < 0 for r in res] and [r for r in res2 if r >= 0] == [r for r in res if r >= 0]
+        assert [o for r, o in zip(res2, outs2) if r >= 0] == [o for r, o in zip(res, outs) if r >= 0]
     for c, cap, r, o in zip(comp, caps, res, outs):
         er, eo = (oracle.decode_known if known else oracle.decode_unknown)(c, cap)
         assert (r < 0) == (er < 0), (r, er)
@@ -205,7 +206,7 @@ def test_decode_corrupt_streams_never_escape(known):
 def test_decode_unaligned_stream_start(skew):
     raws = [cases.content(m, 9000, seed=skew).tobytes() for m in cases.MODELS]
     comp = [oracle.encode(d)[1] for d in raws]
-    for lanes in (16, 116, 108):
+    for lanes in (16, 116, 108, 1, 2):
         res, outs = emu.decode(comp, [len(d) for d in raws], lanes=lanes, known=True, sched_seed=skew, src_skew=skew)
         assert outs == raws and res == [len(c) for c in comp]
 
@@ -218,9 +219,29 @@ def test_decode_long_overlapping_matches():
         pat = rng.integers(0, 256, off, dtype=np.uint8)
         raws.append(np.tile(pat, 9000 // off + 2)[:9000].tobytes())
     comp = [oracle.encode(d)[1] for d in raws]
-    for lanes in (32, 16, 8, 4, 132, 116, 108, 104):
+    for lanes in (32, 16, 8, 4, 132, 116, 108, 104, 1, 2):
         res, outs = emu.decode(comp, [len(d) for d in raws], lanes=lanes, known=True, sched_seed=lanes)
         assert outs == raws
+
+
+def test_decode_lane_per_block_fuzz():
+    """The lane-per-block decoder over random content models, lengths, stream / output alignments, ring geometries and
+    lane schedules, for both decoders and both encoders' streams: every lane walks its own block, so blocks of very
+    different cost share a warp (literal runs and matches longer than 64 bytes go through the warp-wide copy)."""
+    rng = np.random.default_rng(77)
+    for trial in range(24):
+        raws = []
+        for _ in range(int(rng.integers(20, 70))):
+            n = int(rng.choice([int(rng.integers(1, 40)), int(rng.integers(40, 2000)), int(rng.integers(2000, 20000))]))
+            raws.append(cases.content(str(rng.choice(cases.MODELS)), n, seed=int(rng.integers(1 << 30))).tobytes())
+        comp = [(oracle.encode_hc if rng.integers(2) else oracle.encode)(d)[1] for d in raws]
+        known = bool(rng.integers(2))
+        caps = [len(d) if known else len(d) + int(rng.integers(0, 40)) for d in raws]
+        res, outs = emu.decode(comp, caps, lanes=int(rng.choice([1, 2])), known=known, sched_seed=int(rng.integers(1, 1 << 20)),
+                               src_skew=int(rng.integers(0, 16)), dst_skew=int(rng.integers(0, 16)))
+        for c, d, cap, r, o in zip(comp, raws, caps, res, outs):
+            assert r == (len(c) if known else len(d)), (trial, len(d), r)
+            assert o[:len(d)] == d, (trial, len(d))
 
 
 # ---- LZ4HC (one thread per block: the device source compiled as plain scalar code) ------------------------------------
