@@ -66,7 +66,7 @@ struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
     DevBuf src, dst, meta, packed, offs, scan;
-    PinBuf hmeta;
+    PinBuf hmeta, bounce;
 };
 
 }  // namespace
@@ -79,6 +79,7 @@ struct lz4b200_ctx {
     int next_counter = 0;
     DevBuf hc_arena, compact_tmp, enc_arena;
     cudaEvent_t hc_done = nullptr;         // the HC state arena is shared: HC launches are chained through this event
+    cudaEvent_t compact_done = nullptr;    // likewise the scan scratch of lz4b200_compact
     int decode_lanes = 16;                 // lanes per block for device-memory batches (+100 = output-staged variant)
     bool decode_lanes_auto = true;         // host-memory batches: chosen per chunk from the compression ratio
     int encode_ctas_per_sm = 0;            // encoder warps (= blocks in flight) per SM: 0 = the default; up to 14 keep their table in shared memory, up to 28 in all
@@ -105,7 +106,7 @@ struct DeviceGuard {
 // Decode group size from the ratio compressed/raw of a batch (tools/sweep.py): incompressible data is long literal runs
 // (whole warps, 128-bit copies), nearly-empty streams are long matches, everything between is sequence-dense (the
 // denser, the smaller the group: 8 lanes around ratio 0.58, 4 lanes around 0.37; both output-staged).
-int lanes_for_ratio(double ratio) { return ratio > 0.95 ? 32 : (ratio < 0.05 ? 16 : (ratio < 0.45 ? 104 : 108)); }
+int lanes_for_ratio(double ratio, int64_t n_blocks) { (void)n_blocks; return ratio > 0.95 ? 32 : (ratio < 0.05 ? 16 : (ratio < 0.45 ? 104 : 108)); }
 
 int run_device(lz4b200_ctx* c, const BatchArgs& a, int op /*0 enc fast, 1 enc hc, 2 dec known, 3 dec unknown*/, cudaStream_t st, int lanes = 0)
 {
@@ -143,35 +144,52 @@ int run_device(lz4b200_ctx* c, const BatchArgs& a, int op /*0 enc fast, 1 enc hc
 }
 
 // Host-memory batch: chunked, overlapped H2D / kernel / D2H.
+// Only bytes a block PRODUCED ever reach the caller's buffer (the reference's safe codec leaves everything behind the
+// return value untouched, its native ones spill at most 7 bytes): known-size decodes produce exactly dst_cap[i] bytes per
+// block, so maximal runs of adjacent slots go back in one transfer each; encoders and the unknown-size decoder are
+// compacted on the device (the same kernel as the packed encode), cross PCIe as one packed transfer into a pinned bounce
+// buffer and are scattered to dst + dst_off[i] from there.  Chunks of at most 8 blocks copy block by block.
 int run_host(lz4b200_ctx* c, const uint8_t* src, const int64_t* src_off, const int32_t* src_len,
              uint8_t* dst, const int64_t* dst_off, const int32_t* dst_cap, int32_t* out_len, int32_t n, int op)
 {
     const bool decode = op >= 2;
     int32_t b0 = 0; int k = 0;
-    // Large chunks copy every maximal run of adjacent destination slots back in one transfer (bytes of a slot beyond
-    // the block's return value are unspecified, as with the reference's native codecs); small ones wait for the
-    // per-block results and copy exactly the produced bytes.
-    struct Pending { int32_t b0, b1; int64_t dlo; bool contiguous; int32_t* h_out; };
+    enum Mode { PER_BLOCK, RUNS, PACKED };
+    struct Pending { int32_t b0, b1; int64_t dlo; Mode mode; int32_t* h_out; int64_t* h_off; };
     Pending pend[NSLOT]; bool busy[NSLOT] = {false, false, false};
+    // whatever happens, nothing of this call is still in flight when it returns (the staging buffers are reused)
+    struct Drain { lz4b200_ctx* c; ~Drain() { for (int i = 0; i < NSLOT; i++) cudaStreamSynchronize(c->slot[i].stream); } } drain{c};
 
     auto retire = [&](int s) -> int {
         // outputs of slot s are on the host once its event has fired; scatter out_len and (if needed) per-block payloads
         if (!busy[s]) return LZ4B200_OK;
-        CU(cudaEventSynchronize(c->slot[s].done));
+        busy[s] = false;
+        Slot& sl = c->slot[s];
+        CU(cudaEventSynchronize(sl.done));
         Pending& p = pend[s];
-        std::memcpy(out_len + p.b0, p.h_out, sizeof(int32_t) * (size_t)(p.b1 - p.b0));
-        if (!p.contiguous) {
-            // slots with gaps between them: copy exactly the bytes each block produced, nothing in between
+        const int32_t m = p.b1 - p.b0;
+        std::memcpy(out_len + p.b0, p.h_out, sizeof(int32_t) * (size_t)m);
+        if (p.mode == PER_BLOCK) {
             for (int32_t i = p.b0; i < p.b1; i++) {
                 int32_t r = out_len[i];
-                int64_t nbytes = decode ? (op == 2 ? (r >= 0 ? dst_cap[i] : 0) : std::max(r, 0)) : std::max(r, 0);
+                int64_t nbytes = op == 2 ? (r >= 0 ? dst_cap[i] : 0) : std::max(r, 0);
                 if (nbytes > 0)
-                    CU(cudaMemcpyAsync(dst + dst_off[i], (uint8_t*)c->slot[s].dst.p + (dst_off[i] - p.dlo), (size_t)nbytes,
-                                       cudaMemcpyDeviceToHost, c->slot[s].stream));
+                    CU(cudaMemcpyAsync(dst + dst_off[i], (uint8_t*)sl.dst.p + (dst_off[i] - p.dlo), (size_t)nbytes,
+                                       cudaMemcpyDeviceToHost, sl.stream));
             }
-            CU(cudaStreamSynchronize(c->slot[s].stream));
+            CU(cudaStreamSynchronize(sl.stream));
+        } else if (p.mode == PACKED) {
+            const int64_t total = p.h_off[m];
+            if (total > 0) {
+                CU(sl.bounce.reserve((size_t)total));
+                CU(cudaMemcpyAsync(sl.bounce.p, sl.packed.p, (size_t)total, cudaMemcpyDeviceToHost, sl.stream));
+                CU(cudaStreamSynchronize(sl.stream));
+                for (int32_t i = 0; i < m; i++) {
+                    const int64_t nb = p.h_off[i + 1] - p.h_off[i];
+                    if (nb > 0) std::memcpy(dst + dst_off[p.b0 + i], (const uint8_t*)sl.bounce.p + p.h_off[i], (size_t)nb);
+                }
+            }
         }
-        busy[s] = false;
         return LZ4B200_OK;
     };
 
@@ -187,20 +205,21 @@ int run_host(lz4b200_ctx* c, const uint8_t* src, const int64_t* src_off, const i
         int rc = retire(s); if (rc) return rc;
         Slot& sl = c->slot[s];
         const int32_t m = b1 - b0;
-        int64_t slo = INT64_MAX, shi = INT64_MIN, dlo = INT64_MAX, dhi = INT64_MIN; bool contiguous = true;
+        int64_t slo = INT64_MAX, shi = INT64_MIN, dlo = INT64_MAX, dhi = INT64_MIN;
         for (int32_t i = b0; i < b1; i++) {
             if (src_len[i] < 0 || dst_cap[i] < 0) return fail(LZ4B200_E_ARG, "negative block length");
             slo = std::min(slo, src_off[i]); shi = std::max(shi, src_off[i] + src_len[i]);
             dlo = std::min(dlo, dst_off[i]); dhi = std::max(dhi, dst_off[i] + dst_cap[i]);
         }
-        contiguous = m > 8;
+        const Mode mode = m <= 8 ? PER_BLOCK : (op == 2 ? RUNS : PACKED);
         const size_t sbytes = (size_t)(shi - slo), dbytes = (size_t)(dhi - dlo);
         CU(sl.src.reserve(sbytes + 64)); CU(sl.dst.reserve(dbytes + 64));
-        const size_t meta_bytes = (size_t)m * (8 + 4 + 8 + 4 + 4);
+        const size_t meta_bytes = (size_t)m * (8 + 4 + 8 + 4 + 4) + sizeof(int64_t) * (size_t)(m + 2);
         CU(sl.meta.reserve(meta_bytes)); CU(sl.hmeta.reserve(meta_bytes));
-        // meta layout: int64 src_off[m] | int64 dst_off[m] | int32 src_len[m] | int32 dst_cap[m] | int32 out_len[m]
+        // meta layout: int64 src_off[m] | int64 dst_off[m] | int32 src_len[m] | int32 dst_cap[m] | int32 out_len[m] | (host only) int64 packed_off[m+1]
         int64_t* h_so = (int64_t*)sl.hmeta.p; int64_t* h_do = h_so + m;
         int32_t* h_sl = (int32_t*)(h_do + m); int32_t* h_dc = h_sl + m; int32_t* h_out = h_dc + m;
+        int64_t* h_off = (int64_t*)(((uintptr_t)(h_out + m) + 7) & ~(uintptr_t)7);
         for (int32_t i = 0; i < m; i++) {
             h_so[i] = src_off[b0 + i] - slo; h_do[i] = dst_off[b0 + i] - dlo;
             h_sl[i] = src_len[b0 + i]; h_dc[i] = dst_cap[b0 + i];
@@ -217,11 +236,18 @@ int run_host(lz4b200_ctx* c, const uint8_t* src, const int64_t* src_off, const i
         if (decode && c->decode_lanes_auto) {
             double cs = 0, rs = 0;
             for (int32_t i = b0; i < b1; i++) { cs += src_len[i]; rs += dst_cap[i]; }
-            lanes = lanes_for_ratio(rs > 0 ? cs / rs : 1.0);
+            lanes = lanes_for_ratio(rs > 0 ? cs / rs : 1.0, m);
         }
         rc = run_device(c, a, op, sl.stream, lanes); if (rc) return rc;
+        if (mode == PACKED) {
+            CU(sl.packed.reserve(dbytes + 64)); CU(sl.offs.reserve(sizeof(int64_t) * (size_t)(m + 1))); CU(sl.scan.reserve(compact_tmp_bytes(m)));
+            cudaError_t e = launch_compact(a.dst, a.dst_off, a.out_len, (uint8_t*)sl.packed.p, (int64_t*)sl.offs.p, m,
+                                           sl.scan.p, sl.scan.cap, c->dev, sl.stream, &c->launches);
+            if (e != cudaSuccess) return cuda_fail(e, "compact launch");
+            CU(cudaMemcpyAsync(h_off, sl.offs.p, sizeof(int64_t) * (size_t)(m + 1), cudaMemcpyDeviceToHost, sl.stream));
+        }
         CU(cudaMemcpyAsync(h_out, a.out_len, sizeof(int32_t) * (size_t)m, cudaMemcpyDeviceToHost, sl.stream));
-        if (contiguous) {
+        if (mode == RUNS) {
             int32_t r0 = b0;
             for (int32_t i = b0 + 1; i <= b1; i++) {
                 if (i == b1 || dst_off[i] != dst_off[i - 1] + dst_cap[i - 1]) {
@@ -232,7 +258,7 @@ int run_host(lz4b200_ctx* c, const uint8_t* src, const int64_t* src_off, const i
             }
         }
         CU(cudaEventRecord(sl.done, sl.stream));
-        pend[s] = Pending{b0, b1, dlo, contiguous, h_out}; busy[s] = true;
+        pend[s] = Pending{b0, b1, dlo, mode, h_out, h_off}; busy[s] = true;
         b0 = b1;
     }
     for (int i = 0; i < NSLOT; i++) { int rc = retire((k + i) % NSLOT); if (rc) return rc; }
@@ -249,6 +275,7 @@ int run_host_encode_packed(lz4b200_ctx* c, const uint8_t* src, const int64_t* sr
     int32_t b0 = 0; int k = 0; int64_t written = 0;
     struct Pending { int32_t b0, b1; int32_t* h_out; int64_t* h_off; };
     Pending pend[NSLOT]; bool busy[NSLOT] = {false, false, false};
+    struct Drain { lz4b200_ctx* c; ~Drain() { for (int i = 0; i < NSLOT; i++) cudaStreamSynchronize(c->slot[i].stream); } } drain{c};
 
     auto retire = [&](int s) -> int {
         if (!busy[s]) return LZ4B200_OK;
@@ -335,18 +362,22 @@ int batch(lz4b200_ctx* c, const void* src, const int64_t* src_off, const int32_t
     return run_host(c, (const uint8_t*)src, src_off, src_len, (uint8_t*)dst, dst_off, dst_cap, out_len, n, op);
 }
 
-std::mutex g_default_mu;
-lz4b200_ctx* g_default = nullptr;
+// The single-block entry points are re-entrant like the reference's (SURVEY 8b "Threading"): every calling thread gets
+// a context of its own (streams + staging buffers), created on first use and destroyed with the thread.
+struct ThreadCtx {
+    lz4b200_ctx* c = nullptr;
+    ~ThreadCtx() { if (c) lz4b200_destroy(c); }
+};
+thread_local ThreadCtx g_thread_ctx;
 
 lz4b200_ctx* default_ctx()
 {
-    std::lock_guard<std::mutex> lock(g_default_mu);
-    if (!g_default) {
+    if (!g_thread_ctx.c) {
         int dev = 0;
         if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
-        if (lz4b200_create(&g_default, dev) != LZ4B200_OK) g_default = nullptr;
+        if (lz4b200_create(&g_thread_ctx.c, dev) != LZ4B200_OK) g_thread_ctx.c = nullptr;
     }
-    return g_default;
+    return g_thread_ctx.c;
 }
 
 int single(const char* source, char* dest, int isize, int ocap, int op)
@@ -402,6 +433,7 @@ int lz4b200_create(lz4b200_ctx** out, int device)
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(&c->counters, sizeof(uint32_t) * NCOUNTER);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->hc_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->compact_done, cudaEventDisableTiming);
     for (int i = 0; i < NSLOT && e == cudaSuccess; i++) {
         e = cudaStreamCreateWithFlags(&c->slot[i].stream, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->slot[i].done, cudaEventDisableTiming);
@@ -418,12 +450,13 @@ void lz4b200_destroy(lz4b200_ctx* c)
     cudaDeviceSynchronize();
     for (int i = 0; i < NSLOT; i++) {
         Slot& s = c->slot[i];
-        s.src.release(); s.dst.release(); s.meta.release(); s.hmeta.release(); s.packed.release(); s.offs.release(); s.scan.release();
+        s.src.release(); s.dst.release(); s.meta.release(); s.hmeta.release(); s.packed.release(); s.offs.release(); s.scan.release(); s.bounce.release();
         if (s.done) cudaEventDestroy(s.done);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     c->hc_arena.release(); c->compact_tmp.release(); c->enc_arena.release();
     if (c->hc_done) cudaEventDestroy(c->hc_done);
+    if (c->compact_done) cudaEventDestroy(c->compact_done);
     if (c->counters) cudaFree(c->counters);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -474,10 +507,14 @@ int lz4b200_compact(lz4b200_ctx* c, const void* slots, const int64_t* slot_off, 
     std::lock_guard<std::mutex> lock(c->mu);
     DeviceGuard g(c->device);
     cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) { CU(cudaMemsetAsync(out_off, 0, sizeof(int64_t), st)); return LZ4B200_OK; }     // out_off[0] = total = 0
     if (compact_tmp_bytes(n) > c->compact_tmp.cap) { CU(cudaDeviceSynchronize()); CU(c->compact_tmp.reserve(compact_tmp_bytes(n))); }
+    // one scan scratch per context: compactions on different streams are serialised on it
+    CU(cudaStreamWaitEvent(st, c->compact_done, 0));
     cudaError_t e = launch_compact((const uint8_t*)slots, slot_off, len, (uint8_t*)packed, out_off, n,
                                    c->compact_tmp.p, c->compact_tmp.cap, c->dev, st, &c->launches);
     if (e != cudaSuccess) return cuda_fail(e, "compact launch");
+    CU(cudaEventRecord(c->compact_done, st));
     return LZ4B200_OK;
 }
 

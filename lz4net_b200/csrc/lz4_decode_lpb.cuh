@@ -98,6 +98,10 @@ SIMT_DEV void lpb_decode_warp(LpbShared<GEO>* sh, const LpbBatch& a, uint32_t* c
     auto fetch = [&](int lo, int p) {
         const uint32_t q = (uint32_t)p + skew;
         if (q < iland) return;
+        // Units requested earlier may still be in flight towards slots the new requests will use (the ring window moves up
+        // to `lo`, possibly past units that were requested but never read): two copies in flight to one slot land in no
+        // defined order, so what is in flight is drained first.
+        simt::cp_async_commit(); simt::cp_async_wait<0>();
         const uint32_t start = ((uint32_t)lo + skew) & ~15u;
         if (start > ifill) ifill = start;                          // units below are never read
         refill(start);
@@ -163,6 +167,7 @@ SIMT_DEV void lpb_decode_warp(LpbShared<GEO>* sh, const LpbBatch& a, uint32_t* c
                     total = (skew + (uint32_t)isize + 15u) & ~15u;
                     a0 = (uint32_t)((uintptr_t)dst & 15); gbase = dst - a0;
                     ip = 0; vop = fpos = slo = a0; phase = 0; coop = 0;
+                    simt::cp_async_commit(); simt::cp_async_wait<0>();     // (units the previous block requested but never read)
                     ifill = 0; refill(0);
                     active = true; fresh = true;
                 }
@@ -277,7 +282,10 @@ SIMT_DEV void lpb_decode_warp(LpbShared<GEO>* sh, const LpbBatch& a, uint32_t* c
             simt::syncwarp(FULL);                                           // the copy -> lane k's later loads
         }
         if (active && coop != 0) {
-            if (coop == 1) ip += clen;                                      // (the next fetch repositions the input ring behind the run)
+            if (coop == 1) {                                                // the input ring jumps behind the run (drains what is in flight first)
+                ip += clen;
+                if (phase == 1) fetch(ip, ip + 8 < isize ? ip + 8 : isize - 1);
+            }
             else phase = 0;
             vop += (uint32_t)clen; fpos = slo = vop;                        // the ring holds nothing of the block any more
             coop = 0;

@@ -110,7 +110,15 @@ namespace simt {
 struct PendingCopy { void* dst; const void* src; };
 static std::deque<std::vector<PendingCopy>> g_groups[32];
 static std::vector<PendingCopy> g_open[32];
-void cp_async16_emu(void* sdst, const void* gsrc) { g_open[simt_emu::current_lane()].push_back(PendingCopy{sdst, gsrc}); }
+void cp_async16_emu(void* sdst, const void* gsrc)
+{
+    const int l = simt_emu::current_lane();
+    // two copies in flight to the same shared-memory unit land in no defined order on the device: a bug, whatever the
+    // emulator's own (in-order) completion would make of it
+    for (const auto& g : g_groups[l]) for (const PendingCopy& c : g) if (c.dst == sdst) { fprintf(stderr, "simt_emu: two cp.async in flight to one shared-memory unit (lane %d)\n", l); abort(); }
+    for (const PendingCopy& c : g_open[l]) if (c.dst == sdst) { fprintf(stderr, "simt_emu: two cp.async in flight to one shared-memory unit (lane %d)\n", l); abort(); }
+    g_open[l].push_back(PendingCopy{sdst, gsrc});
+}
 void cp_async_commit_emu() { int l = simt_emu::current_lane(); g_groups[l].push_back(g_open[l]); g_open[l].clear(); }
 void cp_async_wait_emu(int n)
 {
