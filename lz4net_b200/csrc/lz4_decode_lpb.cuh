@@ -9,15 +9,18 @@
 // sequences of 32 different blocks; the per-sequence chain (token -> lengths -> offset -> copy) is SIMT-parallel
 // across blocks instead of being repeated per block.
 //
-// Data flow per lane (all of it private to the lane, no warp collective on the common path):
-//   compressed stream --cp.async, 16 B per request, issued a full iteration ahead--> a 256 B input ring in shared memory
-//   -> header bytes by LDS; literals ring -> output ring, matches output ring -> output ring, in 32-bit words with the
-//   source funnel-shifted into the destination's alignment (SHF), bytes only for heads, tails and overlaps < 8;
-//   output ring (the last OUT bytes of the block: the window that serves every match with offset <= OUT - 8)
-//   --LDS.128 + STG.128, 64 B at a time--> global memory.  Matches further back read the lane's own earlier output
-//   from global memory (same thread: program order is enough).
-// The lanes' rings are laid out 16 bytes past a multiple of 128 apart, so that the 128-bit accesses of the fills and
-// flushes are conflict-free and word accesses of lanes in lock step are spread over eight bank groups.
+// Data flow per lane:
+//   compressed stream --cp.async, 16 B per request, issued a full iteration ahead--> a private 256 B input ring
+//   (shared memory, rows 16 bytes past a multiple of 128 apart) -> header bytes by LDS;
+//   literals (input ring) and matches (output ring) are APPENDED to the output ring in aligned 32-bit words only: the
+//   source is read as aligned words and funnel-shifted (SHF) to the destination's byte phase, the bytes that do not
+//   fill a word yet are carried in a register and written through -- no byte loops for heads and tails;
+//   the output ring holds the last OUT bytes of the block (the window that serves every match up to OUT - 8 back).
+//   It is laid out word-skewed across the warp -- word w of lane l lives in row w, column (l + w) mod 32 -- so that
+//   the lanes' own accesses are bank-conflict free when they run in lock step AND a whole row of one lane can be read
+//   by the warp without conflicts: finished 128-byte chunks leave for global memory through quarter-warp transposed
+//   reads and fully coalesced 128-bit stores (four lanes' chunks per step).
+//   Matches further back than the window read the lane's earlier output from global memory.
 // Runs that a single lane would take too long over (literal runs and matches longer than 64 bytes -- incompressible
 // stretches, RLE) are handed to the whole warp: the lane publishes (source, destination, length, offset), the warp
 // copies with coalesced 128-bit moves (lz4_copy.cuh), and the lane carries on behind the run.
@@ -34,16 +37,20 @@ namespace lz4b200 {
 template <int IN_, int OUT_>
 struct LpbGeom {
     static constexpr int IN = IN_, OUT = OUT_;
-    static constexpr int LANE_BYTES = IN + OUT + 16;               // == 16 (mod 128)
+    static constexpr int IN_STRIDE = IN + 16;                      // == 16 (mod 128): the 128-bit fills of the eight lanes of a phase never collide
     static constexpr int MAXL = 64, MAXM = 64;                     // longest literal run / match a lane copies by itself
     static constexpr int LOOK = 1 + 1 + MAXL + 2 + 1 + 4;          // stream bytes such a sequence can touch (+ word over-read)
     static constexpr int WIN = OUT - 8;                            // matches up to this far back are served by the output ring
-    static constexpr int FLUSH = 64;                               // bytes written out per flush step
-    static_assert((IN & (IN - 1)) == 0 && (OUT & (OUT - 1)) == 0 && (IN + OUT) % 128 == 0, "ring sizes");
-    static_assert(IN >= 3 * LOOK + 16 && OUT >= FLUSH + MAXL + MAXM + 16, "ring capacity");     // (unflushed bytes never exceed FLUSH - 1 + one sequence)
+    static constexpr int CHUNK = 128;                              // flush unit (bytes, aligned in the output buffer)
+    static constexpr int HIGH = OUT - 256 > CHUNK ? OUT - 256 : CHUNK;   // a lane with this many unflushed bytes forces a flush step
+    static_assert((IN & (IN - 1)) == 0 && (OUT & (OUT - 1)) == 0 && OUT >= 256, "ring sizes");
+    static_assert(IN >= 3 * LOOK + 16 && HIGH + MAXL + MAXM <= OUT, "ring capacity");
 };
 
-template <class GEO> struct alignas(16) LpbShared { uint8_t lane[32][GEO::LANE_BYTES]; };
+template <class GEO> struct alignas(128) LpbShared {
+    uint8_t out[32 * GEO::OUT];                                    // the warp's output rings, word-skewed (see above)
+    uint8_t in[32][GEO::IN_STRIDE];                                // the lanes' input rings
+};
 
 struct LpbBatch {
     const uint8_t* src; const int64_t* src_off; const int32_t* src_len;
@@ -51,39 +58,46 @@ struct LpbBatch {
     int32_t* out_len; int32_t n_blocks;
 };
 
+template <int K> struct LpbKind { static constexpr int value = K; };
+
 // One warp: every lane decodes blocks of its own, taken from the global counter, until the batch is exhausted.
 template <bool KNOWN, class GEO>
 SIMT_DEV void lpb_decode_warp(LpbShared<GEO>* sh, const LpbBatch& a, uint32_t* counter, int lane)
 {
     constexpr uint32_t FULL = 0xFFFFFFFFu;
-    constexpr uint32_t IMASK = GEO::IN - 1, OMASK = GEO::OUT - 1;
+    constexpr uint32_t IMASK = GEO::IN - 1;
     constexpr int LEN_LIMIT = 0x3FFFFFFF;
-    const simt::smem_ref ir = simt::smem_ref_of(sh->lane[lane]);
-    const simt::smem_ref orr = simt::smem_ref_of(sh->lane[lane] + GEO::IN);
+    const simt::smem_ref ir = simt::smem_ref_of(sh->in[lane]);
+    const simt::smem_ref ow = simt::smem_ref_of(sh->out);
+    const uint32_t l4 = 4u * (uint32_t)lane;
+    // byte offset (inside `out`) of the aligned word holding virtual position v4 (a multiple of 4) of the lane whose 4 * index is lane4
+    auto oword = [](uint32_t lane4, uint32_t v4) -> uint32_t { return ((v4 & (uint32_t)(GEO::OUT - 4)) << 5) + ((lane4 + v4) & 124u); };
 
     // ---- lane state -------------------------------------------------------------------------------------------------
     bool active = false, drained = false;
     uint32_t blk = 0;
     const uint8_t* abase = nullptr;     // compressed stream, rounded down to 16 bytes
-    uint8_t* gbase = nullptr;           // output block, rounded down to 16 bytes
+    uint8_t* gbase = nullptr;           // output block, rounded down to 128 bytes
     uint32_t skew = 0, total = 0;       // src - abase; round_up16(skew + isize)
     uint32_t a0 = 0;                    // dst - gbase: "virtual" output position v = op + a0, so that gbase + v is the address
     int isize = 0, cap = 0;
     int ip = 0;                         // read cursor (stream position)
     uint32_t vop = 0;                   // write cursor (virtual)
+    uint32_t acc = 0;                   // the bytes of the word at vop & ~3 written so far (low vop & 3 bytes, the rest zero)
     uint32_t fpos = 0;                  // virtual position up to which the output is in global memory
     uint32_t slo = 0;                   // lowest virtual position whose byte is (still) valid in the output ring
     uint32_t ifill = 0;                 // aligned stream offset (from abase) of the next 16-byte unit to request
     uint32_t f1 = 0;                    // ifill at the last commit
     uint32_t iland = 0;                 // every unit below this offset has landed in the ring
-    int phase = 0;                      // 0: a sequence header comes next; 1: offset + match of the current sequence
+    int phase = 0;                      // 0: a sequence header comes next; 1: offset + match of the current sequence; 2: finished
     uint32_t token = 0;
     int coop = 0;                       // 0 none, 1 literal run, 2 match: a copy the whole warp makes for this lane
     int clen = 0; uint32_t coff = 0;
     bool fresh = false;                 // the block was set up in this iteration: its first units have not landed yet
+    bool need_all = false;              // everything of this lane must be in global memory before its next step (end, warp copy, far match)
+    int result = 0; bool done = false;
 
     auto ib = [&](int p) -> uint32_t { return simt::lds_u8(ir, ((uint32_t)p + skew) & IMASK); };
-    auto ob = [&](uint32_t v) -> uint32_t { return simt::lds_u8(orr, v & OMASK); };
     // request every unit that fits: the ring may hold [need & ~15, (need & ~15) + IN) where need = oldest offset still wanted
     auto refill = [&](uint32_t need_off) {
         const uint32_t lim = (need_off & ~15u) + (uint32_t)GEO::IN;
@@ -109,48 +123,57 @@ SIMT_DEV void lpb_decode_warp(LpbShared<GEO>* sh, const LpbBatch& a, uint32_t* c
         f1 = iland = ifill;
     };
     auto ibx = [&](int p) -> uint32_t { fetch(p, p); return ib(p); };
-    // bytes [fpos, hi) of the output ring -> global memory: bytes up to a 16-byte boundary, then 128-bit units
-    auto flush_to = [&](uint32_t hi) {
-        while ((fpos & 15u) && fpos < hi) { simt::stg_u8(gbase + fpos, (uint8_t)ob(fpos)); fpos++; }
-        while (fpos + 64 <= hi) {
-            uint4 v[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) v[k] = simt::lds_v4(orr, (fpos + 16u * k) & OMASK);
-#pragma unroll
-            for (int k = 0; k < 4; k++) simt::stg_v4(gbase + fpos + 16u * k, v[k]);
-            fpos += 64;
+
+    // Aligned source word at position p4 (a multiple of 4) of: K = 0 the input ring (p4 = stream offset from abase),
+    // 1 the lane's output ring (virtual position), 2 the lane's output in global memory (virtual position).
+    auto load_src = [&](auto kind, uint32_t p4) -> uint32_t {
+        constexpr int K = decltype(kind)::value;
+        if (K == 0) return simt::lds_u32(ir, p4 & IMASK);
+        if (K == 1) return simt::lds_u32(ow, oword(l4, p4));
+        return simt::ldg_u32(gbase + p4);
+    };
+    // Append n >= 1 bytes to the output ring: source bytes s .. s+n-1 (K as above; s = stream position for K = 0).
+    // K = 1 requires the source to start at least 8 bytes back (the loop reads one aligned source word ahead).
+    auto append = [&](auto kind, uint32_t s, uint32_t n) {
+        constexpr int K = decltype(kind)::value;
+        const uint32_t sq = K == 0 ? s + skew : s;
+        const uint32_t ssh = (sq & 3u) * 8u;
+        uint32_t sp = sq & ~3u;
+        uint32_t lo = load_src(kind, sp);
+        const uint32_t k = vop & 3u, dsh = k * 8u;
+        uint32_t v4 = vop & ~3u;
+        uint32_t c = dsh ? acc << (32u - dsh) : 0u;                // the carried bytes, moved to the top of a word
+        uint32_t rem = n;
+        while (rem > 4) {                                          // whole groups of 4 source bytes -> one finished word each
+            const uint32_t hi = load_src(kind, sp + 4);
+            const uint32_t x = simt::funnel_r(lo, hi, ssh);
+            lo = hi; sp += 4;
+            simt::sts_u32(ow, oword(l4, v4), simt::funnel_l(c, x, dsh));
+            c = x; v4 += 4; rem -= 4;
         }
-        while (fpos + 16 <= hi) { simt::stg_v4(gbase + fpos, simt::lds_v4(orr, fpos & OMASK)); fpos += 16; }
-    };
-    auto flush_all = [&]() {
-        flush_to(vop);
-        while (fpos < vop) { simt::stg_u8(gbase + fpos, (uint8_t)ob(fpos)); fpos++; }
-    };
-    // n bytes -> output ring at virtual position v.  SRC: 0 input ring (stream position s), 1 output ring (virtual position
-    // s, at least 8 back), 2 global memory (virtual position s of the own output, not overlapping the destination)
-    auto src_byte = [&](int kind, uint32_t s) -> uint32_t {
-        return kind == 0 ? simt::lds_u8(ir, (s + skew) & IMASK) : (kind == 1 ? simt::lds_u8(orr, s & OMASK) : (uint32_t)simt::ldg_u8(gbase + s));
-    };
-    auto src_word = [&](int kind, uint32_t s4) -> uint32_t {       // aligned word holding source index s4 (ring offset / address rounded down)
-        return kind == 0 ? simt::lds_u32(ir, ((s4 + skew) & ~3u) & IMASK)
-             : (kind == 1 ? simt::lds_u32(orr, (s4 & ~3u) & OMASK) : simt::ldg_u32(gbase + (s4 & ~3u)));
-    };
-    auto copy_in = [&](int kind, uint32_t s, uint32_t v, uint32_t n) {
-        uint32_t i = 0;
-        if (n >= 8) {
-            while ((v + i) & 3u) { simt::sts_u8(orr, (v + i) & OMASK, src_byte(kind, s + i)); i++; }
-            // the source as aligned words, funnel-shifted: bytes s+i .. s+i+3 = (lo, hi) >> 8 * misalignment
-            const uint32_t mis = kind == 0 ? ((s + i + skew) & 3u) : ((s + i) & 3u);
-            const uint32_t sh8 = mis * 8u;
-            uint32_t lo = src_word(kind, s + i);
-            for (; i + 4 <= n; i += 4) {
-                const uint32_t hi = mis ? src_word(kind, s + i + 4) : 0u;
-                simt::sts_u32(orr, (v + i) & OMASK, simt::funnel_r(lo, hi, sh8));
-                lo = mis ? hi : src_word(kind, s + i + 4);
-            }
+        {                                                          // the last group: 1..4 bytes
+            const uint32_t hi = load_src(kind, sp + 4);
+            uint32_t x = simt::funnel_r(lo, hi, ssh);
+            if (rem < 4) x &= (1u << (8u * rem)) - 1u;
+            const uint32_t carried = dsh ? c >> (32u - dsh) : 0u;
+            const uint32_t w = carried | (x << dsh);
+            simt::sts_u32(ow, oword(l4, v4), w);
+            if (k + rem >= 4) {                                    // the word is finished; what spilled over starts the next one
+                acc = dsh ? x >> (32u - dsh) : 0u;
+                if (k + rem > 4) simt::sts_u32(ow, oword(l4, v4 + 4), acc);      // written through
+            } else acc = w;
         }
-        for (; i < n; i++) simt::sts_u8(orr, (v + i) & OMASK, src_byte(kind, s + i));
+        vop += n;
     };
+    // one byte (overlapping matches closer than 8 bytes; sources that straddle the ring's valid range)
+    auto append_byte = [&](uint32_t b) {
+        const uint32_t k = vop & 3u;
+        acc |= b << (8u * k);
+        simt::sts_u32(ow, oword(l4, vop & ~3u), acc);
+        if (k == 3) acc = 0;
+        vop++;
+    };
+    auto ring_byte = [&](uint32_t v) -> uint32_t { return (simt::lds_u32(ow, oword(l4, v & ~3u)) >> (8u * (v & 3u))) & 255u; };
 
     for (;;) {
         // ---------------- idle lanes take the next block ----------------
@@ -165,8 +188,8 @@ SIMT_DEV void lpb_decode_warp(LpbShared<GEO>* sh, const LpbBatch& a, uint32_t* c
                 else {
                     skew = (uint32_t)((uintptr_t)src & 15); abase = src - skew;
                     total = (skew + (uint32_t)isize + 15u) & ~15u;
-                    a0 = (uint32_t)((uintptr_t)dst & 15); gbase = dst - a0;
-                    ip = 0; vop = fpos = slo = a0; phase = 0; coop = 0;
+                    a0 = (uint32_t)((uintptr_t)dst & 127); gbase = dst - a0;
+                    ip = 0; vop = fpos = slo = a0; acc = 0; phase = 0; coop = 0; need_all = false; done = false;
                     simt::cp_async_commit(); simt::cp_async_wait<0>();     // (units the previous block requested but never read)
                     ifill = 0; refill(0);
                     active = true; fresh = true;
@@ -180,11 +203,10 @@ SIMT_DEV void lpb_decode_warp(LpbShared<GEO>* sh, const LpbBatch& a, uint32_t* c
         else { simt::cp_async_wait<1>(); iland = f1; f1 = ifill; }  // (all groups but the one just committed are complete: everything below the previous commit's ifill)
         fresh = false;
 
-        int result = 0; bool done = false;
-        if (active) {
-            const int op = (int)(vop - a0);
+        if (active && !need_all) {
             // ---------------- header + literals ----------------
             if (phase == 0) {
+                const int op = (int)(vop - a0);
                 if (ip < isize) fetch(ip, ip + GEO::LOOK < isize ? ip + GEO::LOOK : isize - 1);
                 if (ip >= isize) { result = -ip - 1; done = true; }
                 else {
@@ -208,10 +230,7 @@ SIMT_DEV void lpb_decode_warp(LpbShared<GEO>* sh, const LpbBatch& a, uint32_t* c
                         if (!ok) { result = -ip - 1; done = true; }
                         else {
                             if (L > GEO::MAXL) { coop = 1; clen = L; }     // the warp copies it: src + ip -> dst + op
-                            else {
-                                copy_in(0, (uint32_t)ip, vop, (uint32_t)L);
-                                ip += L; vop += (uint32_t)L;
-                            }
+                            else if (L > 0) { append(LpbKind<0>(), (uint32_t)ip, (uint32_t)L); ip += L; }
                             phase = last ? 2 : 1;
                         }
                     }
@@ -221,39 +240,41 @@ SIMT_DEV void lpb_decode_warp(LpbShared<GEO>* sh, const LpbBatch& a, uint32_t* c
             if (!done && coop == 0 && phase == 1) {
                 const int op1 = (int)(vop - a0);
                 fetch(ip, ip + 8 < isize ? ip + 8 : isize - 1);
-                uint32_t off = ib(ip) | (ib(ip + 1) << 8); ip += 2;         // :862 / :982 (ip + 2 <= isize was checked with the literals)
-                if (off == 0 || off > (uint32_t)op1) { result = -ip - 1; done = true; }          // :863 / :983 (offset 0 rejected by design)
+                const uint32_t off = ib(ip) | (ib(ip + 1) << 8);            // :862 / :982 (ip + 2 <= isize was checked with the literals)
+                int q = ip + 2;
+                if (off == 0 || off > (uint32_t)op1) { result = -q - 1; done = true; }          // :863 / :983 (offset 0 rejected by design)
                 else {
                     int M = (int)(token & 15);
                     if (M == 15) {                                          // :866 / :986-999
                         uint32_t s = 255;
-                        if (KNOWN) { do { if (ip >= isize || M > LEN_LIMIT) { M = -1; break; } s = ibx(ip++); M += (int)s; } while (s == 255); }
-                        else       { while (ip < isize - 6 && M <= LEN_LIMIT) { s = ibx(ip++); M += (int)s; if (s != 255) break; } }
-                        if (M < 0 || M > LEN_LIMIT) { result = -ip - 1; done = true; }
+                        if (KNOWN) { do { if (q >= isize || M > LEN_LIMIT) { M = -1; break; } s = ibx(q++); M += (int)s; } while (s == 255); }
+                        else       { while (q < isize - 6 && M <= LEN_LIMIT) { s = ibx(q++); M += (int)s; if (s != 255) break; } }
+                        if (M < 0 || M > LEN_LIMIT) { result = -q - 1; done = true; }
                     }
-                    if (!done && M > cap - op1) { result = -ip - 1; done = true; }
+                    if (!done && M > cap - op1) { result = -q - 1; done = true; }
                     if (!done) {
                         const int n = M + 4;
-                        if (op1 + n > cap - 5) { result = -ip - 1; done = true; }               // :893 / :1025 -- the last 5 bytes are literals
-                        else if (n > GEO::MAXM) { coop = 2; clen = n; coff = off; }
-                        else {
-                            const uint32_t s = vop - off;
-                            if (off <= (uint32_t)GEO::WIN && s >= slo) {
-                                if (off >= 8) copy_in(1, s, vop, (uint32_t)n);
-                                else for (int i = 0; i < n; i++) simt::sts_u8(orr, (vop + (uint32_t)i) & OMASK, ob(s + (uint32_t)i));   // overlap: byte by byte, in order
-                            } else if (off > (uint32_t)GEO::WIN) {
-                                // beyond the window: in global memory for good (off > WIN >= n: no overlap with the destination,
-                                // and everything below vop - WIN + n was flushed long ago)
-                                copy_in(2, s, vop, (uint32_t)n);
-                            } else {
-                                // just behind a run the warp copied: the source straddles the ring's valid range
+                        const uint32_t s = vop - off;
+                        if (op1 + n > cap - 5) { result = -q - 1; done = true; }                // :893 / :1025 -- the last 5 bytes are literals
+                        else if (n > GEO::MAXM) { coop = 2; clen = n; coff = off; ip = q; }
+                        else if (off <= (uint32_t)GEO::WIN) {
+                            if (s >= slo && off >= 8) append(LpbKind<1>(), s, (uint32_t)n);
+                            else {
+                                // overlap closer than 8, or a source that straddles the start of the ring's valid range (just
+                                // behind a run the warp copied -- what lies below is in global memory): byte by byte, in order
                                 for (int i = 0; i < n; i++) {
                                     const uint32_t p = s + (uint32_t)i;
-                                    simt::sts_u8(orr, (vop + (uint32_t)i) & OMASK, p >= slo ? ob(p) : (uint32_t)simt::ldg_u8(gbase + p));
+                                    append_byte(p >= slo ? ring_byte(p) : (uint32_t)simt::ldg_u8(gbase + p));
                                 }
                             }
-                            vop += (uint32_t)n;
-                            phase = 0;
+                            ip = q; phase = 0;
+                        } else if (s + (uint32_t)n > fpos) {
+                            // a source behind the window that is not in global memory yet: write this lane out completely
+                            // first and take the sequence again in the next iteration
+                            need_all = true;
+                        } else {
+                            append(LpbKind<2>(), s, (uint32_t)n);         // off > WIN >= n: no overlap with the destination
+                            ip = q; phase = 0;
                         }
                     }
                 }
@@ -262,9 +283,55 @@ SIMT_DEV void lpb_decode_warp(LpbShared<GEO>* sh, const LpbBatch& a, uint32_t* c
                 result = KNOWN ? ip : (int)(vop - a0);
                 done = true;
             }
-            if (done || coop) flush_all();                                  // the warp's copy / the end of the block: everything out
-            else if (vop - fpos >= (uint32_t)GEO::FLUSH) flush_to(vop & ~15u);
+            if (done || coop) need_all = true;                              // the end of the block / the warp's copy: everything out first
         }
+        // ---------------- finished chunks -> global memory, four lanes per step --------------------------------------------
+        // A step serves, per quarter warp, the lowest lane of that quarter that wants it: its eight lanes read 16 bytes each
+        // of that lane's ring (transposed: conflict free) and store 128 contiguous bytes.  Steps run when enough lanes have
+        // a finished chunk (lock-step data: all of them at once), when a lane's backlog nears the ring's capacity, or when
+        // a lane must be written out completely.
+        {
+            const uint32_t pend = active ? vop - fpos : 0u;
+            const uint32_t ready = simt::ballot(FULL, active && (vop >> 7) > (fpos >> 7));
+            const uint32_t urgent = simt::ballot(FULL, active && (pend >= (uint32_t)GEO::HIGH || (need_all && pend > 0)));
+            if (urgent || simt::popc(ready) >= 16) {
+                const uint32_t qbase = (uint32_t)lane & 24u, j = (uint32_t)lane & 7u;
+                for (;;) {
+                    const bool want = active && (need_all ? vop > fpos : (vop >> 7) > (fpos >> 7));
+                    const uint32_t m = simt::ballot(FULL, want);
+                    if (!m) break;
+                    const uint32_t mq = (m >> qbase) & 255u;
+                    const int k = mq ? (int)qbase + simt::ffs(mq) - 1 : lane;       // the lane this quarter serves (none: itself, nothing to do)
+                    const uint32_t klo = simt::shfl(FULL, fpos, k);
+                    const uint32_t kvop = simt::shfl(FULL, vop, k);
+                    const uint64_t gb = (uint64_t)(uintptr_t)gbase;
+                    uint8_t* const kg = (uint8_t*)(uintptr_t)(((uint64_t)simt::shfl(FULL, (uint32_t)(gb >> 32), k) << 32) | simt::shfl(FULL, (uint32_t)gb, k));
+                    if (mq) {
+                        const uint32_t cb = klo & ~127u;
+                        uint32_t khi = cb + 128u; if (khi > kvop) khi = kvop;       // (only a lane that is written out completely ends inside a chunk)
+                        const uint32_t b = cb + 16u * j;
+                        const uint32_t k4 = 4u * (uint32_t)k;
+                        if (b >= klo && b + 16u <= khi) {
+                            uint4 v;
+                            v.x = simt::lds_u32(ow, oword(k4, b)); v.y = simt::lds_u32(ow, oword(k4, b + 4));
+                            v.z = simt::lds_u32(ow, oword(k4, b + 8)); v.w = simt::lds_u32(ow, oword(k4, b + 12));
+                            simt::stg_v4(kg + b, v);
+                        } else if (b + 16u > klo && b < khi) {                      // the edges of the range: words, then bytes
+                            for (uint32_t t = 0; t < 16; t += 4) {
+                                const uint32_t ws = b + t;
+                                if (ws + 4 <= klo || ws >= khi) continue;
+                                const uint32_t w = simt::lds_u32(ow, oword(k4, ws));
+                                if (ws >= klo && ws + 4 <= khi) simt::stg_u32(kg + ws, w);
+                                else for (uint32_t e = 0; e < 4; e++) if (ws + e >= klo && ws + e < khi) simt::stg_u8(kg + ws + e, (uint8_t)(w >> (8u * e)));
+                            }
+                        }
+                        if (lane == k) fpos = khi;
+                    }
+                }
+                simt::syncwarp(FULL);                                       // the stores above -> the served lanes' later loads of their own output
+            }
+        }
+        if (active && need_all && !done && coop == 0) need_all = false;     // (a far match waited for its source: take the sequence again)
         // ---------------- runs the whole warp copies ----------------
         uint32_t req = simt::ballot(FULL, active && coop != 0);
         while (req) {
@@ -276,7 +343,6 @@ SIMT_DEV void lpb_decode_warp(LpbShared<GEO>* sh, const LpbBatch& a, uint32_t* c
             const uint64_t spk = (uint64_t)(uintptr_t)(abase + skew + (uint32_t)ip);
             uint8_t* const d = (uint8_t*)(uintptr_t)(((uint64_t)simt::shfl(FULL, (uint32_t)(dpk >> 32), k) << 32) | simt::shfl(FULL, (uint32_t)dpk, k));
             const uint8_t* const s = (const uint8_t*)(uintptr_t)(((uint64_t)simt::shfl(FULL, (uint32_t)(spk >> 32), k) << 32) | simt::shfl(FULL, (uint32_t)spk, k));
-            simt::syncwarp(FULL);                                           // lane k's flush -> everybody's loads
             if (kind == 1) { InputSrc sp{s}; group_copy<32, false>(d, sp, n, lane, FULL); }
             else group_copy_match<32>(d, o, n, lane, FULL);
             simt::syncwarp(FULL);                                           // the copy -> lane k's later loads
@@ -285,13 +351,17 @@ SIMT_DEV void lpb_decode_warp(LpbShared<GEO>* sh, const LpbBatch& a, uint32_t* c
             if (coop == 1) {                                                // the input ring jumps behind the run (drains what is in flight first)
                 ip += clen;
                 if (phase == 1) fetch(ip, ip + 8 < isize ? ip + 8 : isize - 1);
+            } else phase = 0;
+            vop += (uint32_t)clen; fpos = slo = vop; acc = 0;               // the ring holds nothing of the block any more ...
+            if (vop & 3u) {                                                 // ... except the started word, which later appends complete
+                acc = simt::ldg_u32(gbase + (vop & ~3u)) & ((1u << (8u * (vop & 3u))) - 1u);
+                simt::sts_u32(ow, oword(l4, vop & ~3u), acc);
+                slo = vop & ~3u;
             }
-            else phase = 0;
-            vop += (uint32_t)clen; fpos = slo = vop;                        // the ring holds nothing of the block any more
-            coop = 0;
-            if (phase == 2) { flush_all(); result = KNOWN ? ip : (int)(vop - a0); done = true; }
+            coop = 0; need_all = false;
+            if (phase == 2) { result = KNOWN ? ip : (int)(vop - a0); done = true; }
         }
-        if (active && done) { simt::stg_u32(a.out_len + blk, (uint32_t)result); active = false; }
+        if (active && done) { simt::stg_u32(a.out_len + blk, (uint32_t)result); active = false; done = false; }
         // ---------------- ask for the units the next iterations will read ----------------
         if (active) refill((uint32_t)ip + skew);
     }
