@@ -82,9 +82,9 @@ struct lz4b200_ctx {
     cudaEvent_t compact_done = nullptr;    // likewise the scan scratch of lz4b200_compact
     int decode_lanes = 16;                 // lanes per block for device-memory batches (+100 = output-staged variant)
     bool decode_lanes_auto = true;         // host-memory batches: chosen per chunk from the compression ratio
-    int encode_ctas_per_sm = 0;            // encoder warps (= blocks in flight) per SM: 0 = the default; up to 14 keep their table in shared memory, up to 28 in all
-    int encode_smem_warps = 0;             // > 0: at most this many warps keep their table in shared memory (test hook for the global-table path)
-    int encode_variant = 2;                // same-hash detection inside a round: 1 exact votes, 2 optimistic (default); +10: exact votes for the global-table warps
+    int encode_ctas_per_sm = 0;            // warp-per-block encoder warps per SM: 0 = as many as shared memory holds tables for (14)
+    int encode_lane_warp = 1;              // the lane-per-block encoder warp next to them: 0 off, 1 for large batches (default), 2 always
+    int encode_variant = 2;                // same-hash detection inside a round: 1 exact votes, 2 optimistic (default)
     int encode_tune[4] = {512, 12, 8, 24}; // prefetch distance, lane_copy_max, probe_max, wide_min (lz4_encode.cuh EncTune)
     size_t host_chunk_bytes = HOST_CHUNK_BYTES_DEFAULT;
     int hc_concurrency = 131072;         // blocks in flight (one thread each, 256 KiB state): 16384 / 65536 / 131072 / 262144 -> 2.8 / 8.3 / 9.7 / 9.7 GB/s (E50)
@@ -114,13 +114,14 @@ int run_device(lz4b200_ctx* c, const BatchArgs& a, int op /*0 enc fast, 1 enc hc
     cudaError_t e = cudaSuccess;
     switch (op) {
     case 0: {
-        // (the global-table arena is written by every launch: launches on different streams of one context are
-        // serialised on it through the same event as the HC arena)
-        const size_t need = encode_arena_bytes(c->encode_ctas_per_sm, c->dev);
-        if (need > c->enc_arena.cap) { CU(cudaDeviceSynchronize()); CU(c->enc_arena.reserve(need)); }
-        if (need) CU(cudaStreamWaitEvent(st, c->hc_done, 0));
-        e = launch_encode_fast(a, c->counter(), c->encode_ctas_per_sm, c->encode_smem_warps, c->encode_tune, c->encode_variant, c->enc_arena.p, c->dev, st, &c->launches);
-        if (need && e == cudaSuccess) e = cudaEventRecord(c->hc_done, st);
+        // (the lane-per-block warp's table arena is written by every launch: launches on different streams of one context
+        // are serialised on it through the same event as the HC arena)
+        const bool lw = c->encode_lane_warp != 0;
+        if (lw && !c->enc_arena.p) { CU(cudaDeviceSynchronize()); CU(c->enc_arena.reserve(encode_arena_bytes(c->dev))); }
+        if (lw) CU(cudaStreamWaitEvent(st, c->hc_done, 0));
+        e = launch_encode_fast(a, c->counter(), c->encode_ctas_per_sm, c->encode_lane_warp, c->encode_tune, c->encode_variant,
+                               lw ? c->enc_arena.p : nullptr, c->dev, st, &c->launches);
+        if (lw && e == cudaSuccess) e = cudaEventRecord(c->hc_done, st);
         break;
     }
     case 1: {
@@ -542,13 +543,13 @@ int lz4b200_set_option(lz4b200_ctx* c, const char* key, int64_t value)
         c->decode_lanes = (int)value; c->decode_lanes_auto = false;
     }
     else if (k == "decode_lanes_auto") { c->decode_lanes_auto = value != 0; }
-    else if (k == "encode_variant") { if (value != 1 && value != 2 && value != 12) return fail(LZ4B200_E_ARG, "encode_variant must be 1, 2 or 12"); c->encode_variant = (int)value; }
+    else if (k == "encode_variant") { if (value != 1 && value != 2) return fail(LZ4B200_E_ARG, "encode_variant must be 1 or 2"); c->encode_variant = (int)value; }
     else if (k == "encode_prefetch") { if (value < -65536 || value > 65536) return fail(LZ4B200_E_ARG, "encode_prefetch out of range"); c->encode_tune[0] = (int)value; }
     else if (k == "encode_lane_copy_max" || k == "encode_probe_max" || k == "encode_wide_min") {
         if (value < 0 || value > 65536) return fail(LZ4B200_E_ARG, "encoder heuristic out of range");
         c->encode_tune[k == "encode_lane_copy_max" ? 1 : (k == "encode_probe_max" ? 2 : 3)] = (int)value;
     }
-    else if (k == "encode_smem_warps") { if (value < 0 || value > 14) return fail(LZ4B200_E_ARG, "encode_smem_warps out of range"); c->encode_smem_warps = (int)value; }
+    else if (k == "encode_lane_warp") { if (value < 0 || value > 2) return fail(LZ4B200_E_ARG, "encode_lane_warp must be 0, 1 or 2"); c->encode_lane_warp = (int)value; }
     else if (k == "encode_ctas_per_sm") { if (value < 0 || value > 32) return fail(LZ4B200_E_ARG, "encode_ctas_per_sm out of range"); c->encode_ctas_per_sm = (int)value; }
     else if (k == "hc_concurrency") {
         if (value < 32 || value > (1 << 20)) return fail(LZ4B200_E_ARG, "hc_concurrency out of range");

@@ -1,99 +1,86 @@
 // encode.cu -- kernels + launchers for the fast and the HC encoders.
 #include "kernels.h"
 #include "lz4_encode.cuh"
+#include "lz4_encode_lpb.cuh"
 #include "lz4hc_encode.cuh"
 
 namespace lz4b200 {
 
-// ---- fast encoder: one warp per block, persistent, dynamic block hand-out --------------------------------------------
-// All encoder warps of an SM live in ONE CTA.  Up to 14 of them keep their 16 KiB position table in shared memory (14 x
-// 16 KiB = 224 KiB of dynamic shared memory; separate CTAs would each pay 1 KiB of system-reserved shared memory, which
-// costs the 14th warp).  The kernel is a per-warp latency chain (throughput is linear in resident warps), so the warps
-// beyond those 14 -- as many as the register file holds at the launch bound NW -- run the same parse with their table
-// in a global-memory arena that stays L2-resident (16 KiB per warp): a table round trip costs them an L2 round trip,
-// but every one of them is one more block in flight.  The warps never synchronise with each other.
+// ---- fast encoder: persistent, dynamic block hand-out ----------------------------------------------------------------
+// All encoder warps of an SM live in ONE CTA.  14 of them are warp-per-block encoders (lz4_encode.cuh) whose 16 KiB
+// position tables fill the shared memory (14 x 16 KiB = 224 KiB of dynamic shared memory; separate CTAs would each pay
+// 1 KiB of system-reserved shared memory, which costs the 14th warp).  That kernel is a per-warp latency chain -- issue
+// slots half idle, and no room for a 15th table -- so an optional 15th warp runs the lane-per-block encoder
+// (lz4_encode_lpb.cuh): 32 more blocks in flight per SM, one per lane, tables in an L2-resident global arena.
+// All warps take blocks from the same counter and never synchronise with each other.
+// (Measured and dropped in round 2: more warp-per-block encoders with their tables in global memory -- 18 / 20 / 24 / 28
+// warps per SM ran at 0.83 / 0.74 / 0.5 / 0.4 of the 14-warp kernel's throughput, profiles/encoder_r02_history.md.)
 constexpr int ENC_SMEM_WARPS = 14;
 
-template <int DUP, int NW, int GDUP>
-__global__ void __launch_bounds__(32 * NW, 1)
-lz4_encode_fast_kernel(BatchArgs a, uint32_t* counter, EncTune tune, int smem_warps, uint8_t* arena)
+template <int DUP, bool LPB>
+__global__ void __launch_bounds__(32 * (ENC_SMEM_WARPS + (LPB ? 1 : 0)), 1)
+lz4_encode_fast_kernel(BatchArgs a, uint32_t* counter, EncTune tune, int warp_warps, uint8_t* arena)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const bool gt = NW > ENC_SMEM_WARPS && warp >= smem_warps;
-    void* table = gt ? (void*)(arena + ((size_t)blockIdx.x * NW + warp) * sizeof(EncShared))
-                     : (void*)((EncShared*)smem + warp);
+    if (LPB && warp >= warp_warps) {
+        const EncLpbBatch b{a.src, a.src_off, a.src_len, a.dst, a.dst_off, a.dst_cap, a.out_len, a.n_blocks};
+        lpb_encode_warp(arena + (size_t)blockIdx.x * 32 * 16384, b, counter, lane);
+        return;
+    }
+    EncShared* sh = (EncShared*)smem + warp;
     for (;;) {
         uint32_t b = 0;
         if (lane == 0) b = atomicAdd(counter, 1u);
         b = simt::shfl(0xFFFFFFFFu, b, 0);
         if (b >= (uint32_t)a.n_blocks) break;
-        int r;
-        if (NW > ENC_SMEM_WARPS && gt)
-            r = encode_block<GDUP, 0, true>(table, a.src + a.src_off[b], a.src_len[b], a.dst + a.dst_off[b], a.dst_cap[b], lane, tune);
-        else
-            r = encode_block<DUP, 0, false>(table, a.src + a.src_off[b], a.src_len[b], a.dst + a.dst_off[b], a.dst_cap[b], lane, tune);
+        const int r = encode_block<DUP, 0>(sh, a.src + a.src_off[b], a.src_len[b], a.dst + a.dst_off[b], a.dst_cap[b], lane, tune);
         if (lane == 0) a.out_len[b] = r;
     }
 }
 
-template <int DUP, int NW, int GDUP>
-static cudaError_t launch_fast_t(const BatchArgs& a, uint32_t* counter, int dyn, long long grid, int warps, int smem_warps,
-                                 uint8_t* arena, const EncTune& tune, cudaStream_t stream)
+template <int DUP, bool LPB>
+static cudaError_t launch_fast_t(const BatchArgs& a, uint32_t* counter, int dyn, long long grid, int warps, uint8_t* arena,
+                                 const EncTune& tune, cudaStream_t stream)
 {
-    cudaError_t e = cudaFuncSetAttribute(lz4_encode_fast_kernel<DUP, NW, GDUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+    cudaError_t e = cudaFuncSetAttribute(lz4_encode_fast_kernel<DUP, LPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
     if (e != cudaSuccess) return e;
-    lz4_encode_fast_kernel<DUP, NW, GDUP><<<(unsigned)grid, 32 * warps, dyn, stream>>>(a, counter, tune, smem_warps, arena);
+    lz4_encode_fast_kernel<DUP, LPB><<<(unsigned)grid, 32 * (warps + (LPB ? 1 : 0)), dyn, stream>>>(a, counter, tune, warps, arena);
     return cudaGetLastError();
 }
 
-size_t encode_arena_bytes(int warps_per_sm, const DeviceInfo& dev)
-{
-    return warps_per_sm > ENC_SMEM_WARPS ? (size_t)28 * dev.num_sms * sizeof(EncShared) : 0;     // one slot per warp of the widest kernel
-}
+size_t encode_arena_bytes(const DeviceInfo& dev) { return (size_t)dev.num_sms * 32 * 16384; }     // one table per lane of the lane-per-block warp
 
-cudaError_t launch_encode_fast(const BatchArgs& a, uint32_t* counter, int warps_per_sm, int smem_warps_max, const int* tune4, int variant,
+cudaError_t launch_encode_fast(const BatchArgs& a, uint32_t* counter, int warps_per_sm, int lane_warp, const int* tune4, int variant,
                                void* arena, const DeviceInfo& dev, cudaStream_t stream, int64_t* launches)
 {
     if (a.n_blocks <= 0) return cudaSuccess;
-    int smem_warps = dev.smem_optin / (int)sizeof(EncShared);
-    if (smem_warps > ENC_SMEM_WARPS) smem_warps = ENC_SMEM_WARPS;
-    if (smem_warps < 1) smem_warps = 1;
-    if (warps_per_sm < 1) warps_per_sm = smem_warps;
-    const int smem_full = smem_warps;
-    if (warps_per_sm > ENC_SMEM_WARPS && smem_warps_max > 0 && smem_warps_max < smem_warps) smem_warps = smem_warps_max;   // (tests: global-table warps in small batches)
-    // the launch bounds the kernel is built for: 14 (all tables in shared memory), 18, 20, 24, 28
-    const int nw = warps_per_sm <= 14 ? 14 : (warps_per_sm <= 18 ? 18 : (warps_per_sm <= 20 ? 20 : (warps_per_sm <= 24 ? 24 : 28)));
-    if (warps_per_sm > nw) warps_per_sm = nw;
-    if (nw == 14 && warps_per_sm > smem_warps) warps_per_sm = smem_warps;
-    if (nw > 14 && (smem_full < ENC_SMEM_WARPS || !arena)) return cudaErrorInvalidValue;
-    // small batches: spread the blocks over the SMs first
+    int max_warps = dev.smem_optin / (int)sizeof(EncShared);
+    if (max_warps > ENC_SMEM_WARPS) max_warps = ENC_SMEM_WARPS;
+    if (max_warps < 1) max_warps = 1;
+    if (warps_per_sm < 1 || warps_per_sm > max_warps) warps_per_sm = max_warps;
+    // small batches: spread the blocks over the SMs first, and leave the lane-per-block warp out (its lanes take a block
+    // each and keep it ~30x longer than a warp does: it pays only when every SM has many blocks to go through)
     long long grid = dev.num_sms;
     int warps = warps_per_sm;
+    bool lpb = lane_warp != 0 && arena != nullptr;
+    if (lane_warp == 1 && a.n_blocks < (long long)dev.num_sms * (warps + 32) * 8) lpb = false;    // (lane_warp == 2 forces it: tests)
     if (a.n_blocks < (long long)dev.num_sms * warps) {
         warps = (int)((a.n_blocks + dev.num_sms - 1) / dev.num_sms);
         grid = (a.n_blocks + warps - 1) / warps;
     }
-    const int sw = warps < smem_warps ? warps : smem_warps;
-    const int dyn = sw * (int)sizeof(EncShared);
+    const int dyn = warps * (int)sizeof(EncShared);
     cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), stream);
     if (e != cudaSuccess) return e;
     if (launches) ++*launches;
     EncTune tune; tune.pf_dist = tune4[0]; tune.lane_copy_max = tune4[1]; tune.probe_max = tune4[2]; tune.wide_min = tune4[3];
     uint8_t* ar = (uint8_t*)arena;
-    // variant % 10: how same-hash iterations of one round are found by the shared-memory warps (lz4_encode.cuh): 1 = always
-    // exact (one vote per hash bit), 2 = through the table, pairs resolved in place; variant / 10 (0 -> 2): the same for
-    // the warps whose table is in global memory
-#define LZ4B200_ENC_CASE(NW_) \
-    case NW_: return variant / 10 == 1 ? launch_fast_t<2, NW_, 1>(a, counter, dyn, grid, warps, sw, ar, tune, stream) \
-                                       : launch_fast_t<2, NW_, 2>(a, counter, dyn, grid, warps, sw, ar, tune, stream);
-    switch (nw) {
-    LZ4B200_ENC_CASE(18) LZ4B200_ENC_CASE(20) LZ4B200_ENC_CASE(24) LZ4B200_ENC_CASE(28)
-    default: break;
-    }
-#undef LZ4B200_ENC_CASE
-    return variant % 10 == 1 ? launch_fast_t<1, 14, 1>(a, counter, dyn, grid, warps, sw, ar, tune, stream)
-                             : launch_fast_t<2, 14, 2>(a, counter, dyn, grid, warps, sw, ar, tune, stream);
+    // variant: how same-hash iterations of one round are found by the warp-per-block encoders (lz4_encode.cuh):
+    // 1 = always exact (one vote per hash bit), 2 = through the table, pairs resolved in place
+    if (lpb) return variant == 1 ? launch_fast_t<1, true>(a, counter, dyn, grid, warps, ar, tune, stream)
+                                 : launch_fast_t<2, true>(a, counter, dyn, grid, warps, ar, tune, stream);
+    return variant == 1 ? launch_fast_t<1, false>(a, counter, dyn, grid, warps, ar, tune, stream)
+                        : launch_fast_t<2, false>(a, counter, dyn, grid, warps, ar, tune, stream);
 }
 
 // ---- HC encoder: one THREAD per block, state arena in global memory -------------------------------------------------

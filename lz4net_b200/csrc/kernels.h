@@ -17,10 +17,11 @@ struct DeviceInfo { int num_sms; int smem_per_sm; int smem_optin; };
 // block hand-out).  They return the launch error (cudaSuccess on success) and add to *launches.
 cudaError_t launch_decode(const BatchArgs& a, bool known_len, int lanes_per_block, uint32_t* counter,
                           const DeviceInfo& dev, cudaStream_t stream, int64_t* launches);
-cudaError_t launch_encode_fast(const BatchArgs& a, uint32_t* counter, int warps_per_sm, int smem_warps_max /* 0 = 14 */, const int* tune4 /* prefetch, lane_copy_max, probe_max, wide_min */, int variant,
-                               void* arena /* encode_arena_bytes(warps_per_sm) of global memory, may be null for <= 14 warps */,
+cudaError_t launch_encode_fast(const BatchArgs& a, uint32_t* counter, int warps_per_sm, int lane_warp /* 0 off, 1 on for large batches, 2 always */,
+                               const int* tune4 /* prefetch, lane_copy_max, probe_max, wide_min */, int variant,
+                               void* arena /* encode_arena_bytes() of global memory for the lane-per-block warp's tables; null = no such warp */,
                                const DeviceInfo& dev, cudaStream_t stream, int64_t* launches);
-size_t      encode_arena_bytes(int warps_per_sm, const DeviceInfo& dev);
+size_t      encode_arena_bytes(const DeviceInfo& dev);
 size_t      hc_scratch_bytes(int concurrency);
 cudaError_t launch_encode_hc(const BatchArgs& a, void* scratch, int concurrency, uint32_t* counter,
                              const DeviceInfo& dev, cudaStream_t stream, int64_t* launches);

@@ -16,10 +16,10 @@
 //   source is read as aligned words and funnel-shifted (SHF) to the destination's byte phase, the bytes that do not
 //   fill a word yet are carried in a register and written through -- no byte loops for heads and tails;
 //   the output ring holds the last OUT bytes of the block (the window that serves every match up to OUT - 8 back).
-//   It is laid out word-skewed across the warp -- word w of lane l lives in row w, column (l + w) mod 32 -- so that
-//   the lanes' own accesses are bank-conflict free when they run in lock step AND a whole row of one lane can be read
-//   by the warp without conflicts: finished 128-byte chunks leave for global memory through quarter-warp transposed
-//   reads and fully coalesced 128-bit stores (four lanes' chunks per step).
+//   The lanes' output rings lie OUT + 4 bytes apart, so word w of lane l sits in bank (l + w) mod 32: the lanes' own
+//   accesses are bank-conflict free when they run in lock step AND consecutive words of one lane can be read by
+//   neighbouring lanes without conflicts: finished 128-byte chunks leave for global memory through quarter-warp
+//   transposed reads and fully coalesced 128-bit stores (four lanes' chunks per step).
 //   Matches further back than the window read the lane's earlier output from global memory.
 // Runs that a single lane would take too long over (literal runs and matches longer than 64 bytes -- incompressible
 // stretches, RLE) are handed to the whole warp: the lane publishes (source, destination, length, offset), the warp
@@ -48,8 +48,8 @@ struct LpbGeom {
 };
 
 template <class GEO> struct alignas(128) LpbShared {
-    uint8_t out[32 * GEO::OUT];                                    // the warp's output rings, word-skewed (see above)
     uint8_t in[32][GEO::IN_STRIDE];                                // the lanes' input rings
+    uint8_t out[32 * (GEO::OUT + 4) + 12];                         // the lanes' output rings, OUT + 4 bytes apart (see above)
 };
 
 struct LpbBatch {
@@ -69,9 +69,9 @@ SIMT_DEV void lpb_decode_warp(LpbShared<GEO>* sh, const LpbBatch& a, uint32_t* c
     constexpr int LEN_LIMIT = 0x3FFFFFFF;
     const simt::smem_ref ir = simt::smem_ref_of(sh->in[lane]);
     const simt::smem_ref ow = simt::smem_ref_of(sh->out);
-    const uint32_t l4 = 4u * (uint32_t)lane;
-    // byte offset (inside `out`) of the aligned word holding virtual position v4 (a multiple of 4) of the lane whose 4 * index is lane4
-    auto oword = [](uint32_t lane4, uint32_t v4) -> uint32_t { return ((v4 & (uint32_t)(GEO::OUT - 4)) << 5) + ((lane4 + v4) & 124u); };
+    const uint32_t l4 = (uint32_t)lane * (uint32_t)(GEO::OUT + 4);
+    // byte offset (inside `out`) of the aligned word holding virtual position v4 (a multiple of 4) of the lane whose ring starts at lane4
+    auto oword = [](uint32_t lane4, uint32_t v4) -> uint32_t { return lane4 + (v4 & (uint32_t)(GEO::OUT - 4)); };
 
     // ---- lane state -------------------------------------------------------------------------------------------------
     bool active = false, drained = false;
@@ -144,6 +144,23 @@ SIMT_DEV void lpb_decode_warp(LpbShared<GEO>* sh, const LpbBatch& a, uint32_t* c
         uint32_t v4 = vop & ~3u;
         uint32_t c = dsh ? acc << (32u - dsh) : 0u;                // the carried bytes, moved to the top of a word
         uint32_t rem = n;
+        // four words per round trip when the source allows reading that far ahead (always for the input ring and global
+        // memory; in the output ring the words read must lie below the write cursor)
+        if (K != 1 || vop - s >= 24u) {
+            while (rem > 16) {
+                uint32_t q[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) q[i] = load_src(kind, sp + 4u + 4u * i);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const uint32_t x = simt::funnel_r(lo, q[i], ssh);
+                    lo = q[i];
+                    simt::sts_u32(ow, oword(l4, v4 + 4u * i), simt::funnel_l(c, x, dsh));
+                    c = x;
+                }
+                sp += 16; v4 += 16; rem -= 16;
+            }
+        }
         while (rem > 4) {                                          // whole groups of 4 source bytes -> one finished word each
             const uint32_t hi = load_src(kind, sp + 4);
             const uint32_t x = simt::funnel_r(lo, hi, ssh);
@@ -301,7 +318,12 @@ SIMT_DEV void lpb_decode_warp(LpbShared<GEO>* sh, const LpbBatch& a, uint32_t* c
                     const uint32_t m = simt::ballot(FULL, want);
                     if (!m) break;
                     const uint32_t mq = (m >> qbase) & 255u;
-                    const int k = mq ? (int)qbase + simt::ffs(mq) - 1 : lane;       // the lane this quarter serves (none: itself, nothing to do)
+                    // the lane this quarter serves (none: itself, nothing to do).  Quarter q starts looking at its lane q: when
+                    // all lanes want (lock step), the four lanes served in one step differ mod 4, so the four quarters' reads
+                    // (each spread over the eight banks of one residue class mod 4) do not collide
+                    const uint32_t qi = qbase >> 3;
+                    const uint32_t rot = ((mq >> qi) | (mq << (8u - qi))) & 255u;
+                    const int k = mq ? (int)(qbase + (((uint32_t)simt::ffs(rot) - 1u + qi) & 7u)) : lane;
                     const uint32_t klo = simt::shfl(FULL, fpos, k);
                     const uint32_t kvop = simt::shfl(FULL, vop, k);
                     const uint64_t gb = (uint64_t)(uintptr_t)gbase;
@@ -310,7 +332,7 @@ SIMT_DEV void lpb_decode_warp(LpbShared<GEO>* sh, const LpbBatch& a, uint32_t* c
                         const uint32_t cb = klo & ~127u;
                         uint32_t khi = cb + 128u; if (khi > kvop) khi = kvop;       // (only a lane that is written out completely ends inside a chunk)
                         const uint32_t b = cb + 16u * j;
-                        const uint32_t k4 = 4u * (uint32_t)k;
+                        const uint32_t k4 = (uint32_t)k * (uint32_t)(GEO::OUT + 4);
                         if (b >= klo && b + 16u <= khi) {
                             uint4 v;
                             v.x = simt::lds_u32(ow, oword(k4, b)); v.y = simt::lds_u32(ow, oword(k4, b + 4));

@@ -74,23 +74,13 @@ SIMT_NOINLINE void copy_long_literals(uint8_t* dst, const uint8_t* src, uint32_t
     group_copy<32, false>(dst, sp, n, lane, 0xFFFFFFFFu);
 }
 
-// The position table: behind a 32-bit shared-window address (GT == false), or in global memory (GT == true: the tables
-// of the warps beyond the 14 that shared memory holds live in an L2-resident arena; a table round trip is then an L2
-// round trip, but the block it belongs to is one more block in flight on the SM).
-template <bool GENERAL, bool GT>
+// The position table behind a 32-bit shared-window address.
+template <bool GENERAL>
 struct EncTable {
-    simt::smem_ref r; uint8_t* g;
-    SIMT_MEM void bind(void* table) { if (GT) g = (uint8_t*)table; else r = simt::smem_ref_of(table); }
-    SIMT_MEM int  get(uint32_t h) const
-    {
-        if (GT) return GENERAL ? (int)simt::ldt_u32(g + h * 4u) : (int)simt::ldt_u16(g + h * 2u);
-        return GENERAL ? (int)simt::lds_u32(r, h * 4u) : (int)simt::lds_u16(r, h * 2u);
-    }
-    SIMT_MEM void put(uint32_t h, int pos) const
-    {
-        if (GT) { if (GENERAL) simt::stt_u32(g + h * 4u, (uint32_t)pos); else simt::stt_u16(g + h * 2u, (uint32_t)pos); }
-        else    { if (GENERAL) simt::sts_u32(r, h * 4u, (uint32_t)pos); else simt::sts_u16(r, h * 2u, (uint32_t)pos); }
-    }
+    simt::smem_ref r;
+    SIMT_MEM void bind(void* table) { r = simt::smem_ref_of(table); }
+    SIMT_MEM int  get(uint32_t h) const { return GENERAL ? (int)simt::lds_u32(r, h * 4u) : (int)simt::lds_u16(r, h * 2u); }
+    SIMT_MEM void put(uint32_t h, int pos) const { if (GENERAL) simt::sts_u32(r, h * 4u, (uint32_t)pos); else simt::sts_u16(r, h * 2u, (uint32_t)pos); }
 };
 
 // One round = W*32 consecutive serial iterations of the find-match loop; lane l evaluates iterations l and (W == 2) 32+l.
@@ -112,8 +102,8 @@ struct RoundOut { int f; bool finished; int ip, ref; };
 
 // SIMPLE: every attempt of the round still has step 1 and lies inside the block (known from two warp-uniform tests):
 // positions are consecutive and every iteration is valid.
-template <bool GENERAL, bool GT, int W, int DUP, int LDP, bool SIMPLE>
-SIMT_DEV RoundOut find_round(const EncTable<GENERAL, GT>& T, const InWords& in, int org, uint32_t A0, bool fused,
+template <bool GENERAL, int W, int DUP, int LDP, bool SIMPLE>
+SIMT_DEV RoundOut find_round(const EncTable<GENERAL>& T, const InWords& in, int org, uint32_t A0, bool fused,
                              int mflimit, int lane, uint32_t lt_mask)
 {
     constexpr uint32_t FULL = 0xFFFFFFFFu;
@@ -255,14 +245,14 @@ SIMT_DEV RoundOut find_round(const EncTable<GENERAL, GT>& T, const InWords& in, 
     }
 }
 
-template <bool GENERAL, bool GT, int DUP, int LDP>
+template <bool GENERAL, int DUP, int LDP>
 SIMT_DEV int encode_block_t(void* table, const uint8_t* src, int n, uint8_t* dst, int cap, int lane, EncTune tune)
 {
     constexpr uint32_t FULL = 0xFFFFFFFFu;
     const int mflimit = n - 12, matchlimit = n - 5;                // :361,:366 / :590,:596
     const uint32_t lt_mask = (1u << lane) - 1u;
     InWords in; in.init(src);
-    EncTable<GENERAL, GT> T; T.bind(table);
+    EncTable<GENERAL> T; T.bind(table);
 
     // sequence queue: lane k holds record k
     int q = 0, op = 0;
@@ -345,9 +335,7 @@ SIMT_DEV int encode_block_t(void* table, const uint8_t* src, int n, uint8_t* dst
         return true;
     };
 
-    for (int i = lane; i < 1024; i += 32) {
-        if (GT) simt::stg_v4((uint4*)table + i, uint4{0, 0, 0, 0}); else ((uint4*)table)[i] = uint4{0, 0, 0, 0};
-    }
+    for (int i = lane; i < 1024; i += 32) ((uint4*)table)[i] = uint4{0, 0, 0, 0};
     simt::syncwarp(FULL);
 
     int anchor = 0;
@@ -383,10 +371,10 @@ SIMT_DEV int encode_block_t(void* table, const uint8_t* src, int n, uint8_t* dst
                 consumed = w2 ? 64 : 32;
                 // step 1 up to attempt 128 (and 2 for attempt 128 itself), everything inside the block?
                 const bool simple = A0 + (uint32_t)consumed - 1u <= 128u && org + (int)A0 - 64 + consumed + 1 <= mflimit;
-                if (w2) r = simple ? find_round<GENERAL, GT, 2, DUP, LDP, true>(T, in, org, A0, fused, mflimit, lane, lt_mask)
-                                   : find_round<GENERAL, GT, 2, DUP, LDP, false>(T, in, org, A0, fused, mflimit, lane, lt_mask);
-                else    r = simple ? find_round<GENERAL, GT, 1, DUP, LDP, true>(T, in, org, A0, fused, mflimit, lane, lt_mask)
-                                   : find_round<GENERAL, GT, 1, DUP, LDP, false>(T, in, org, A0, fused, mflimit, lane, lt_mask);
+                if (w2) r = simple ? find_round<GENERAL, 2, DUP, LDP, true>(T, in, org, A0, fused, mflimit, lane, lt_mask)
+                                   : find_round<GENERAL, 2, DUP, LDP, false>(T, in, org, A0, fused, mflimit, lane, lt_mask);
+                else    r = simple ? find_round<GENERAL, 1, DUP, LDP, true>(T, in, org, A0, fused, mflimit, lane, lt_mask)
+                                   : find_round<GENERAL, 1, DUP, LDP, false>(T, in, org, A0, fused, mflimit, lane, lt_mask);
                 if (r.f < 0) { r.f = 32; consumed = 32; }           // exact path: only the first 32 iterations were evaluated
                 if (r.f >= consumed) {                              // no hit: the find-match loop goes on
                     A0 += (uint32_t)consumed; fused = false; wide = true;
@@ -486,14 +474,14 @@ SIMT_DEV int encode_block_t(void* table, const uint8_t* src, int n, uint8_t* dst
 }
 
 // LZ4_compress_limitedOutput dispatch (original/lz4.c:774-792)
-// `table`: 16 KiB, 16-byte aligned, owned by this warp -- shared memory (GT == false) or global memory (GT == true).
-template <int DUP = 2, int LDP = 0, bool GT = false>
+// `table`: 16 KiB of shared memory, 16-byte aligned, owned by this warp.
+template <int DUP = 2, int LDP = 0>
 SIMT_DEV int encode_block(void* table, const uint8_t* src, int n, uint8_t* dst, int cap, int lane, EncTune tune = EncTune{})
 {
     if (n < 0 || cap < 0) return 0;
     simt::syncwarp(0xFFFFFFFFu);                                   // previous block's table users are done
-    return n < LZ4_64KLIMIT ? encode_block_t<false, GT, DUP, LDP>(table, src, n, dst, cap, lane, tune)
-                            : encode_block_t<true, GT, DUP, LDP>(table, src, n, dst, cap, lane, tune);
+    return n < LZ4_64KLIMIT ? encode_block_t<false, DUP, LDP>(table, src, n, dst, cap, lane, tune)
+                            : encode_block_t<true, DUP, LDP>(table, src, n, dst, cap, lane, tune);
 }
 
 }  // namespace lz4b200

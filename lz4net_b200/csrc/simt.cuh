@@ -71,12 +71,13 @@ SIMT_DEV void sts_u8(smem_ref r, uint32_t off, uint32_t v) { asm volatile("st.sh
 SIMT_DEV void sts_u16(smem_ref r, uint32_t off, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" :: "r"(r.a + off), "h"((uint16_t)v) : "memory"); }
 SIMT_DEV void sts_u32(smem_ref r, uint32_t off, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(r.a + off), "r"(v) : "memory"); }
 
-// position-table entries kept in global memory (encoder warps beyond the ones shared memory holds): written and read
-// back by different lanes of one warp with a __syncwarp() between -- volatile asm so the compiler keeps every access.
-SIMT_DEV uint32_t ldt_u16(const void* p) { uint16_t v; asm volatile("ld.global.u16 %0, [%1];" : "=h"(v) : "l"(p) : "memory"); return v; }
-SIMT_DEV uint32_t ldt_u32(const void* p) { uint32_t v; asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
-SIMT_DEV void stt_u16(void* p, uint32_t v) { asm volatile("st.global.u16 [%0], %1;" :: "l"(p), "h"((uint16_t)v) : "memory"); }
-SIMT_DEV void stt_u32(void* p, uint32_t v) { asm volatile("st.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+// Position-table entries kept in global memory (the lane-per-block encoder): volatile asm so the compiler keeps every
+// access in program order, with an L2 eviction-priority hint (createpolicy evict_last: the tables are the data that must
+// stay L2-resident while the blocks stream through).
+SIMT_DEV uint32_t ldt_hint_u16(const void* p, uint64_t pol) { uint16_t v; asm volatile("ld.global.L2::cache_hint.u16 %0, [%1], %2;" : "=h"(v) : "l"(p), "l"(pol) : "memory"); return v; }
+SIMT_DEV uint32_t ldt_hint_u32(const void* p, uint64_t pol) { uint32_t v; asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol) : "memory"); return v; }
+SIMT_DEV void stt_hint_u16(void* p, uint32_t v, uint64_t pol) { asm volatile("st.global.L2::cache_hint.u16 [%0], %1, %2;" :: "l"(p), "h"((uint16_t)v), "l"(pol) : "memory"); }
+SIMT_DEV void stt_hint_u32(void* p, uint32_t v, uint64_t pol) { asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" :: "l"(p), "r"(v), "l"(pol) : "memory"); }
 
 // Ampere-style asynchronous copy, 16 bytes global -> shared per lane (both addresses 16-byte aligned), tracked per thread:
 // every lane of a warp copies for itself in ONE instruction (the bulk form, UBLKCP, takes uniform operands and would be

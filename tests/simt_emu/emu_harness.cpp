@@ -5,6 +5,7 @@
 #include "lz4_decode.cuh"
 #include "lz4_decode_lpb.cuh"
 #include "lz4_encode.cuh"
+#include "lz4_encode_lpb.cuh"
 #include "lz4hc_encode.cuh"
 #include <stdlib.h>
 #include <vector>
@@ -74,7 +75,6 @@ void lpb_entry(int lane, void* arg)
 }
 
 int g_enc_variant = 2;
-int g_enc_gt = 0;            // 1: the position table is addressed as global memory (the warps beyond the 14 shared-memory ones)
 EncTune g_enc_tune;
 
 struct EncJob {
@@ -86,11 +86,8 @@ void enc_entry(int lane, void* arg)
 {
     EncJob* j = (EncJob*)arg;
     for (int b = 0; b < j->nblocks; b++) {
-        int r;
-        if (g_enc_gt) r = g_enc_variant == 1 ? encode_block<1, 0, true>(j->sh, j->src[b], j->n[b], j->dst[b], j->cap[b], lane, g_enc_tune)
-                                             : encode_block<2, 0, true>(j->sh, j->src[b], j->n[b], j->dst[b], j->cap[b], lane, g_enc_tune);
-        else          r = g_enc_variant == 1 ? encode_block<1>(j->sh, j->src[b], j->n[b], j->dst[b], j->cap[b], lane, g_enc_tune)
-                                             : encode_block<2>(j->sh, j->src[b], j->n[b], j->dst[b], j->cap[b], lane, g_enc_tune);
+        int r = g_enc_variant == 1 ? encode_block<1>(j->sh, j->src[b], j->n[b], j->dst[b], j->cap[b], lane, g_enc_tune)
+                                   : encode_block<2>(j->sh, j->src[b], j->n[b], j->dst[b], j->cap[b], lane, g_enc_tune);
         if (lane == 0) j->result[b] = r;
     }
 }
@@ -124,6 +121,25 @@ void emu_decode_lpb(int geo, int known, int nblocks, const uint8_t* const* src, 
     free(j.sh);
 }
 
+// lane-per-block encoder: the whole warp loop, blocks handed out through the counter
+struct EncLpbJob { EncLpbBatch a; uint32_t counter; uint8_t* tables; };
+void enc_lpb_entry(int lane, void* arg) { EncLpbJob* j = (EncLpbJob*)arg; lpb_encode_warp(j->tables, j->a, &j->counter, lane); }
+
+void emu_encode_lpb(int nblocks, const uint8_t* const* src, const int* n, uint8_t* const* dst, const int* cap,
+                    int* result, uint64_t sched_seed)
+{
+    std::vector<int64_t> so(nblocks), dof(nblocks);
+    const uint8_t* sb = nblocks ? src[0] : nullptr; uint8_t* db = nblocks ? dst[0] : nullptr;
+    for (int i = 0; i < nblocks; i++) { so[i] = src[i] - sb; dof[i] = dst[i] - db; }
+    EncLpbJob j;
+    j.a = EncLpbBatch{sb, so.data(), n, db, dof.data(), cap, result, nblocks};
+    j.counter = 0;
+    j.tables = (uint8_t*)aligned_alloc(128, 32 * 16384);
+    memset(j.tables, 0x5A, 32 * 16384);                 // stale garbage, like a reused arena
+    simt_emu::run_warp(enc_lpb_entry, &j, sched_seed);
+    free(j.tables);
+}
+
 // the HC encoder is one thread per block: plain scalar code, no warp needed
 int emu_encode_hc(const uint8_t* src, int n, uint8_t* dst, int cap)
 {
@@ -134,7 +150,7 @@ int emu_encode_hc(const uint8_t* src, int n, uint8_t* dst, int cap)
     return r;
 }
 
-void emu_set_encode_variant(int v) { g_enc_variant = v % 10; g_enc_gt = v >= 10; }
+void emu_set_encode_variant(int v) { g_enc_variant = v; }
 void emu_set_encode_tune(int lane_copy_max, int probe_max, int wide_min)
 {
     g_enc_tune.lane_copy_max = lane_copy_max; g_enc_tune.probe_max = probe_max; g_enc_tune.wide_min = wide_min;

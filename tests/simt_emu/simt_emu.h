@@ -63,8 +63,10 @@ static inline void sts_u16(smem_ref r, uint32_t off, uint32_t v) { uint16_t t = 
 static inline void sts_u32(smem_ref r, uint32_t off, uint32_t v) { memcpy(r.p + off, &v, 4); }
 static inline uint32_t ldt_u16(const void* p) { uint16_t v; memcpy(&v, p, 2); return v; }
 static inline uint32_t ldt_u32(const void* p) { uint32_t v; memcpy(&v, p, 4); return v; }
-static inline void stt_u16(void* p, uint32_t v) { uint16_t t = (uint16_t)v; memcpy(p, &t, 2); }
-static inline void stt_u32(void* p, uint32_t v) { memcpy(p, &v, 4); }
+static inline uint32_t ldt_hint_u16(const void* p, uint64_t) { return ldt_u16(p); }
+static inline uint32_t ldt_hint_u32(const void* p, uint64_t) { return ldt_u32(p); }
+static inline void stt_hint_u16(void* p, uint32_t v, uint64_t) { uint16_t t = (uint16_t)v; memcpy(p, &t, 2); }
+static inline void stt_hint_u32(void* p, uint32_t v, uint64_t) { memcpy(p, &v, 4); }
 // cp.async: the copy is DEFERRED until the wait that covers its group (per lane), so that code which reads a unit before
 // waiting for it, or overwrites a ring slot that is still to be read, fails in the emulator as well
 void cp_async16_emu(void* sdst, const void* gsrc);
