@@ -50,7 +50,10 @@ def parse():
     p.add_argument("--wave", type=int, default=1 << 18, help="blocks per decode wave (output buffer reuse)")
     p.add_argument("--e2e-blocks", type=int, default=1 << 14)
     p.add_argument("--cpu-blocks", type=int, default=1 << 15)
-    p.add_argument("--lanes", type=int, default=0, help="decode lanes per block (8/16/32); 0 = library default")
+    p.add_argument("--lanes", type=int, default=0, help="decode lanes per block (4/8/16/32, +100 staged, 1/2 lane-per-block); 0 = library default (picked per batch)")
+    p.add_argument("--stream-gib", type=float, default=16.0, help="BASELINE configs[3]: size of the stream that starts on rank 0")
+    p.add_argument("--no-stream", action="store_true")
+    p.add_argument("--no-numa", action="store_true")
     p.add_argument("--enc-ctas", type=int, default=0)
     p.add_argument("--no-sweep", action="store_true")
     p.add_argument("--no-hc", action="store_true")
@@ -187,6 +190,37 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+# host placement: run this rank's threads (and first-touch its pinned staging) on the NUMA node its GPU hangs off
+# ------------------------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa(index: int):
+    """Returns a dict describing what was done.  PCIe traffic of GPUs on the far socket crosses the inter-socket link; with 8
+    ranks each streaming raw + compressed bytes both ways that link, not PCIe, is what the e2e numbers hit first."""
+    info = {"bound": False}
+    try:
+        bus = subprocess.run(["nvidia-smi", "-i", str(index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if not bus:
+            return info
+        dom, rest = bus.split(":", 1)
+        dev = f"{dom[-4:]}:{rest}"
+        node = int(open(f"/sys/bus/pci/devices/{dev}/numa_node").read().strip())
+        info.update({"pci": dev, "numa_node": node})
+        if node < 0:
+            return info
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info.update({"bound": True, "cpus": len(cpus)})
+    except Exception as e:                       # placement is an optimisation, never a reason to fail the run
+        info["error"] = str(e)[:100]
+    return info
+
+
+# ------------------------------------------------------------------------------------------------------------------
 # GPU side
 # ------------------------------------------------------------------------------------------------------------------
 class Workload:
@@ -268,47 +302,153 @@ def measure_pair(work, steps, warmup, hc=False):
     return te / steps, td / steps
 
 
-def e2e_host(ctx, cls, n_blocks, steps, warmup):
-    """The metric through the C ABI with host (pinned) buffers: lz4b200_encode_batch / decode_batch, MEM_HOST."""
-    import numpy as np
-    import torch
-    from lz4net_b200 import synth
-    slot = BLOCK + BLOCK // 255 + 16
-    raw = torch.empty(n_blocks * BLOCK, dtype=torch.uint8).pin_memory()
-    gen = 1024
-    for b0 in range(0, n_blocks, gen):
-        m = min(gen, n_blocks - b0)
-        raw[b0 * BLOCK:(b0 + m) * BLOCK] = torch.from_numpy(synth.make_blocks(cls, m, BLOCK, seed=7, first_block=b0).reshape(-1))
-    comp = torch.empty(n_blocks * slot, dtype=torch.uint8).pin_memory()       # packed payloads land here back to back
-    out = torch.empty(n_blocks * BLOCK, dtype=torch.uint8).pin_memory()
-    so = np.arange(n_blocks, dtype=np.int64) * BLOCK
-    sl = np.full(n_blocks, BLOCK, np.int32); dc = np.full(n_blocks, slot, np.int32)
-    clen = np.zeros(n_blocks, np.int32); used = np.zeros(n_blocks, np.int32); coff = np.zeros(n_blocks + 1, np.int64)
+class E2E:
+    """The metric through the C ABI with HOST buffers: lz4b200_encode_batch_packed + lz4b200_decode_batch (MEM_HOST), every
+    H2D / D2H copy inside the timed calls.  kind: "pinned" (cudaHostAlloc), "pageable" (plain numpy -- what a `fixed` byte[]
+    of a managed caller is), "registered" (pageable, page-locked once with lz4b200_host_register)."""
 
-    def once():
-        t0 = time.perf_counter()
-        # encode: raw blocks in host memory -> packed compressed payloads + offsets in host memory
-        ctx.encode_batch_packed_ptr(raw.data_ptr(), so.ctypes.data, sl.ctypes.data, dc.ctypes.data, comp.data_ptr(), comp.numel(),
-                                    coff.ctypes.data, clen.ctypes.data, n_blocks, hc=False)
-        t1 = time.perf_counter()
-        # decode: the packed payloads -> raw blocks in host memory
-        ctx.decode_batch_ptr(comp.data_ptr(), coff.ctypes.data, clen.ctypes.data, out.data_ptr(), so.ctypes.data, sl.ctypes.data,
-                             used.ctypes.data, n_blocks, known=True, device=False)
-        t2 = time.perf_counter()
-        return t1 - t0, t2 - t1
-    for _ in range(warmup):
-        once()
+    def __init__(self, device, cls, n_blocks, kind="pinned", seed=7):
+        import numpy as np
+        import torch
+        import lz4net_b200
+        from lz4net_b200 import native, synth
+        self.np, self.torch, self.native = np, torch, native
+        self.ctx = lz4net_b200.Context(device)
+        self.n, self.kind = n_blocks, kind
+        slot = BLOCK + BLOCK // 255 + 16
+        def buf(nbytes):
+            if kind == "pinned":
+                return torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+            t = torch.from_numpy(np.empty(nbytes, np.uint8))
+            if kind == "registered":
+                native.check(native.lib().lz4b200_host_register(t.data_ptr(), nbytes), "host_register")
+            return t
+        self.raw, self.comp, self.out = buf(n_blocks * BLOCK), buf(n_blocks * slot), buf(n_blocks * BLOCK)
+        for b0 in range(0, n_blocks, 1024):
+            m = min(1024, n_blocks - b0)
+            self.raw[b0 * BLOCK:(b0 + m) * BLOCK] = torch.from_numpy(synth.make_blocks(cls, m, BLOCK, seed=seed, first_block=b0).reshape(-1))
+        self.so = np.arange(n_blocks, dtype=np.int64) * BLOCK
+        self.sl = np.full(n_blocks, BLOCK, np.int32); self.dc = np.full(n_blocks, slot, np.int32)
+        self.clen = np.zeros(n_blocks, np.int32); self.used = np.zeros(n_blocks, np.int32); self.coff = np.zeros(n_blocks + 1, np.int64)
+
+    def encode(self):
+        self.ctx.encode_batch_packed_ptr(self.raw.data_ptr(), self.so.ctypes.data, self.sl.ctypes.data, self.dc.ctypes.data, self.comp.data_ptr(),
+                                         self.comp.numel(), self.coff.ctypes.data, self.clen.ctypes.data, self.n, hc=False)
+
+    def decode(self):
+        self.ctx.decode_batch_ptr(self.comp.data_ptr(), self.coff.ctypes.data, self.clen.ctypes.data, self.out.data_ptr(), self.so.ctypes.data,
+                                  self.sl.ctypes.data, self.used.ctypes.data, self.n, known=True, device=False)
+
+    def check(self):
+        assert self.torch.equal(self.out, self.raw) and (self.used == self.clen).all(), "e2e round trip failed"
+
+    def close(self):
+        if self.kind == "registered":
+            for t in (self.raw, self.comp, self.out):
+                self.native.lib().lz4b200_host_unregister(t.data_ptr())
+        self.ctx.close()
+
+
+def e2e_sequential(device, cls, n_blocks, steps, warmup, kind="pinned"):
+    """encode then decode, one call after the other (one caller thread)."""
+    w = E2E(device, cls, n_blocks, kind)
     te = td = 0.0
-    for _ in range(steps):
-        a, b = once(); te += a; td += b
-    assert torch.equal(out, raw) and (used == clen).all(), "e2e round trip failed"
-    te /= steps; td /= steps
-    nbytes = n_blocks * BLOCK
-    csum = int(clen.sum())
-    # per step: encode copies raw in / packed payload out; decode copies the packed payload in / raw out
-    h2d = nbytes + csum
-    d2h = csum + nbytes
-    return {"t_enc": te, "t_dec": td, "bytes": nbytes, "h2d": h2d, "d2h": d2h, "compressed": csum}
+    for i in range(warmup + steps):
+        t0 = time.perf_counter(); w.encode(); t1 = time.perf_counter(); w.decode(); t2 = time.perf_counter()
+        if i >= warmup:
+            te += t1 - t0; td += t2 - t1
+    w.check()
+    csum = int(w.clen.sum()); nbytes = n_blocks * BLOCK
+    w.close()
+    return {"t_enc": te / steps, "t_dec": td / steps, "bytes": nbytes, "h2d": nbytes + csum, "d2h": csum + nbytes}
+
+
+def e2e_pipelined(device, cls, n_blocks, steps, warmup):
+    """Two caller threads with a context each (the library's contexts serialise their callers): the encode of step i+1 runs
+    while step i is decoded, so both PCIe directions carry raw + compressed bytes at the same time instead of one direction
+    idling per call.  Returns seconds per step (one step = one encode + one decode of n_blocks blocks)."""
+    a, b = E2E(device, cls, n_blocks, "pinned", seed=7), E2E(device, cls, n_blocks, "pinned", seed=8)
+    a.encode(); b.encode()                       # both batches hold valid streams before the pipeline starts
+    def run(k):
+        # step 2j uses batch a, step 2j+1 batch b; decode(i) overlaps encode(i+1)
+        t = [None]
+        def enc(w): w.encode()
+        for i in range(k):
+            cur, nxt = (a, b) if i % 2 == 0 else (b, a)
+            th = threading.Thread(target=enc, args=(nxt,)); th.start()
+            cur.decode(); th.join()
+    run(max(warmup, 1) * 2)
+    t0 = time.perf_counter(); run(steps * 2); dt = time.perf_counter() - t0
+    a.check(); b.check()
+    csum = int(a.clen.sum()); nbytes = n_blocks * BLOCK
+    a.close(); b.close()
+    # 2 * steps decodes and 2 * steps encodes ran: per step (one encode + one decode) that is dt / (2 * steps)
+    return {"t_step": dt / (2 * steps), "bytes": nbytes, "h2d": nbytes + csum, "d2h": csum + nbytes}
+
+
+def stream_section(ctx, args, rank, world, dev):
+    """BASELINE configs[3]: ONE stream that starts on rank 0, chunked into 64 KiB blocks, encoded by all ranks, payloads back
+    on rank 0 in stream order -- and the mirror image.  Strong scaling: the stream is the same size whatever the world size.
+    Device-timed per phase (CUDA events on the stream the NCCL calls are ordered with), max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from lz4net_b200 import batch, shard, synth
+    nb = int(args.stream_gib * (1 << 30)) // BLOCK
+    enc, dec = shard.gpu_codec(ctx, BLOCK)
+    raw = None
+    if rank == 0:
+        raw = torch.empty(nb * BLOCK, dtype=torch.uint8, device=dev)
+        for b0 in range(0, nb, 65536):
+            batch.synth_fill(ctx, raw[b0 * BLOCK:], min(65536, nb - b0), BLOCK, synth.CLASS_ID[args.cls], seed=6, first_block=b0)
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+    best = None
+    for it in range(2):                                         # the first pass warms NCCL's connections up
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1, e2 = ev(), ev(), ev()
+        e0.record()
+        if world > 1:
+            lens, off, packed = shard.encode_stream_sharded(raw, nb, BLOCK, enc, rank, world, device=dev)
+        else:
+            packed, lens = enc(raw, nb)
+        e1.record()
+        if world > 1:
+            back = shard.decode_stream_sharded(packed, lens, nb, BLOCK, dec, rank, world, device=dev)
+        else:
+            back = dec(packed, lens, nb)
+        e2.record(); torch.cuda.synchronize()
+        te, td = shard.reduce_max([e0.elapsed_time(e1) * 1e-3, e1.elapsed_time(e2) * 1e-3], device="cuda")
+        best = (te, td)
+    res = None
+    if rank == 0:
+        ok = bool(torch.equal(back, raw))
+        # sampled byte identity with the one-GPU encode of the same blocks (rank 0 encodes the sample by itself)
+        idx = list(range(0, nb, max(nb // 64, 1)))[:64]
+        sample = torch.cat([raw[i * BLOCK:(i + 1) * BLOCK] for i in idx])
+        sp, sl = enc(sample, len(idx))
+        so = torch.zeros(len(idx) + 1, dtype=torch.int64, device=dev); so[1:] = torch.cumsum(sl.to(torch.int64), 0)
+        offs = torch.zeros(nb + 1, dtype=torch.int64, device=dev); offs[1:] = torch.cumsum(lens.to(torch.int64), 0)
+        same = True
+        for j, i in enumerate(idx):
+            a0, a1 = int(offs[i]), int(offs[i + 1]); b0, b1 = int(so[j]), int(so[j + 1])
+            same = same and (a1 - a0 == b1 - b0) and bool(torch.equal(packed[a0:a1], sp[b0:b1]))
+        n = nb * BLOCK; comp = int(packed.numel())
+        far = (world - 1) / world
+        te, td = best
+        res = {"workload": f"{args.stream_gib:g} GiB stream of class {args.cls} on rank 0, 64 KiB blocks: NCCL scatter -> encode on {world} GPU(s) -> gather; and back",
+               "scaling": "strong", "n_gpus": world, "ratio": round(comp / n, 4),
+               "encode_gbs": round(n / te / GB, 1), "decode_gbs": round(n / td / GB, 1), "roundtrip_gbs": round(n / (te + td) / GB, 1),
+               "roundtrip_exact": ok, "stream_parity": bool(same), "stream_parity_blocks": len(idx),
+               # what crosses the root's NVLink ports per direction and phase, and the rate that alone would allow
+               "root_link": {"encode_out_bytes": int(n * far), "encode_in_bytes": int(comp * far), "decode_out_bytes": int(comp * far), "decode_in_bytes": int(n * far),
+                             "decode_in_gbs_if_only_transfer": None if world == 1 else round(n * far / td / GB, 1)},
+               "limiter": "none (one GPU: no transfer)" if world == 1 else
+                          "the root's NVLink ports: every raw byte leaves rank 0 before it is encoded and comes back to it after it is decoded (kernel time is 1/N of the one-GPU time)"}
+    del raw
+    torch.cuda.empty_cache()
+    return res
 
 
 def main():
@@ -316,24 +456,27 @@ def main():
     if args.impl == "reference":
         run_reference(args)
         return
-    import torch
-    import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    numa = {"bound": False} if args.no_numa else bind_to_gpu_numa(local)     # before any pinned allocation (first touch)
+    import torch
+    import torch.distributed as dist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: lz4net_b200 has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("nccl", device_id=dev)
     import lz4net_b200
     ctx = lz4net_b200.Context(local)
-    # decode group size per entropy class (tools/sweep.py, profiles/sweep_r01.txt): lanes per block, +100 = the
-    # shared-memory output-staged variant.  Long-run data wants whole warps, sequence-dense data sub-warp groups.
+    # The headline runs the library's DEFAULTS: for device batches the decoder is picked per batch on the device from the
+    # compression ratio.  TUNED_LANES (tools/sweep.py) is what a caller who knows the data could set by hand; the entropy
+    # sweep reports both side by side.
     TUNED_LANES = {"E0": 32, "E50": 108, "E100": 16, "ETEXT": 104}
-    lanes_for = lambda cls: args.lanes or TUNED_LANES[cls]
-    ctx.set_option("decode_lanes", lanes_for(args.cls))
+    if args.lanes:
+        ctx.set_option("decode_lanes", args.lanes)
     if args.enc_ctas:
         ctx.set_option("encode_ctas_per_sm", args.enc_ctas)
     peaks = {}
@@ -381,8 +524,8 @@ def main():
     enc_gbs = total_raw / t_enc / GB; dec_gbs = total_raw / t_dec / GB
     # roofline (per GPU): algorithmic bytes = raw + compressed, both directions of each kernel
     alg = (total_raw + csum_all) / world
-    # DRAM traffic per launch from the committed ncu --set full capture (per-block bytes x blocks in the launch); only
-    # meaningful for the class it was captured on
+    # DRAM traffic per launch: NOT measured in this run -- scaled per block from the committed ncu --set full capture
+    # (profiles/ncu_traffic.json, class E50 only), labelled as such
     traffic_dec = traffic_enc = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
@@ -391,47 +534,82 @@ def main():
             traffic_enc = int(tj["lz4_encode_fast_kernel"]["dram_bytes"] / tj["blocks"] * args.blocks)
     except Exception:
         pass
+    tsrc = "static: profiles/ncu_traffic.json (ncu --set full, bytes per block x blocks per launch), not measured in this run"
     roof_dec = {"kernel": "lz4_decode_kernel", "bound": "hbm", "achieved": round(alg / t_dec / GB, 1), "peak": peak_hbm, "unit": "GB/s",
-                "frac": round(alg / t_dec / GB / peak_hbm, 4), "traffic": traffic_dec, "peak_source": peak_src,
+                "frac": round(alg / t_dec / GB / peak_hbm, 4), "traffic": traffic_dec, "traffic_source": tsrc, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": int(alg / nw), "launch_ms": round(t_dec / nw * 1e3, 3)}
     roof_enc = {"kernel": "lz4_encode_fast_kernel", "bound": "hbm", "achieved": round(alg / t_enc / GB, 1), "peak": peak_hbm, "unit": "GB/s",
-                "frac": round(alg / t_enc / GB / peak_hbm, 4), "traffic": traffic_enc, "peak_source": peak_src,
+                "frac": round(alg / t_enc / GB / peak_hbm, 4), "traffic": traffic_enc, "traffic_source": tsrc, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": int(alg), "launch_ms": round(t_enc * 1e3, 3)}
+    del work
+    torch.cuda.empty_cache()
 
     # ---- end to end through the C ABI with host buffers (every rank, concurrently) -----------------------------------
     e2e = None
     if not args.no_e2e:
-        r = e2e_host(ctx, args.cls, min(args.e2e_blocks, args.blocks), max(2, args.steps // 2), 1)
-        te, td = r["t_enc"], r["t_dec"]
-        te, td = shard.reduce_max([te, td], device="cuda")
-        e2e = {"value": round(r["bytes"] * world / (te + td) / GB, 3), "unit": "GB/s", "h2d_bytes_per_step": int(r["h2d"]),
-               "d2h_bytes_per_step": int(r["d2h"]), "encode_gbs": round(r["bytes"] * world / te / GB, 3),
-               "decode_gbs": round(r["bytes"] * world / td / GB, 3),
-               "sample": f"{min(args.e2e_blocks, args.blocks)} x 64 KiB blocks per GPU in pinned host memory through lz4b200_encode_batch_packed + lz4b200_decode_batch (MEM_HOST), wall clock"}
+        nb_e = min(args.e2e_blocks, args.blocks); st_e = max(2, args.steps // 4)
+        if world > 1:
+            dist.barrier()
+        r = e2e_sequential(local, args.cls, nb_e, st_e, 1, "pinned")
+        if world > 1:
+            dist.barrier()
+        pl = e2e_pipelined(local, args.cls, nb_e, st_e, 1)
+        if world > 1:
+            dist.barrier()
+        pg = e2e_sequential(local, args.cls, min(nb_e, 4096), 2, 1, "pageable")
+        if world > 1:
+            dist.barrier()
+        rg = e2e_sequential(local, args.cls, min(nb_e, 4096), 2, 1, "registered")
+        te, td, tp, tpg, trg = shard.reduce_max([r["t_enc"], r["t_dec"], pl["t_step"], pg["t_enc"] + pg["t_dec"], rg["t_enc"] + rg["t_dec"]], device="cuda")
+        seq = r["bytes"] * world / (te + td) / GB; pip = r["bytes"] * world / tp / GB
+        e2e = {"value": round(max(seq, pip), 3), "unit": "GB/s", "h2d_bytes_per_step": int(r["h2d"]), "d2h_bytes_per_step": int(r["d2h"]),
+               "sequential_gbs": round(seq, 3), "pipelined_gbs": round(pip, 3),
+               "encode_gbs": round(r["bytes"] * world / te / GB, 3), "decode_gbs": round(r["bytes"] * world / td / GB, 3),
+               "pageable_gbs": round(pg["bytes"] * world / tpg / GB, 3), "registered_gbs": round(rg["bytes"] * world / trg / GB, 3),
+               "numa": numa,
+               "sample": f"{nb_e} x 64 KiB blocks per GPU through lz4b200_encode_batch_packed + lz4b200_decode_batch (MEM_HOST), wall clock, every copy inside the calls. "
+                         "value = the better of: sequential (one caller thread: encode, then decode) and pipelined (two caller threads, a context each: the encode of step i+1 "
+                         "overlaps the decode of step i, both PCIe directions busy). pinned host memory; pageable_gbs / registered_gbs: the sequential form from plain "
+                         "malloc'ed memory (what a managed caller's fixed byte[] is) and from the same memory page-locked once with lz4b200_host_register (4096 blocks)"}
+
+    # ---- entropy sweep (BASELINE configs[4]) on every rank: library defaults and hand-tuned decode lanes side by side ----
+    extras = {}
+    if not args.no_sweep:
+        sweep = {}
+        for cls in ("E0", "E50", "E100", "ETEXT"):
+            w = Workload(ctx, min(args.sweep_blocks, args.blocks), cls, args.wave, seed=2, first_block=rank * min(args.sweep_blocks, args.blocks))
+            ctx.set_option("decode_lanes_auto", 1)
+            cs = w.verify()
+            te, td = measure_pair(w, 3, 2)
+            ctx.set_option("decode_lanes", TUNED_LANES[cls])
+            _, td_t = measure_pair(w, 3, 1)
+            ctx.set_option("decode_lanes_auto", 1)
+            te, td, td_t = shard.reduce_max([te, td, td_t], device="cuda")
+            cs_all, = shard.reduce_sum([float(cs)], device="cuda")
+            rb = w.n * BLOCK * world
+            sweep[cls] = {"ratio": round(cs_all / rb, 4), "encode_gbs": round(rb / te / GB, 1), "decode_gbs": round(rb / td / GB, 1),
+                          "decode_roofline_frac": round((rb + cs_all) / td / GB / peak_hbm / world, 4),
+                          "encode_roofline_frac": round((rb + cs_all) / te / GB / peak_hbm / world, 4), "blocks_per_gpu": w.n,
+                          "decode_tuned_gbs": round(rb / td_t / GB, 1), "decode_tuned_lanes": TUNED_LANES[cls],
+                          "decode_tuned_roofline_frac": round((rb + cs_all) / td_t / GB / peak_hbm / world, 4)}
+            del w; torch.cuda.empty_cache()
+        if args.lanes:
+            ctx.set_option("decode_lanes", args.lanes)
+        extras["entropy_sweep"] = sweep
+        extras["entropy_sweep_note"] = f"aggregate over {world} GPU(s), device-timed, max over ranks; decode_gbs = library default (decoder picked on the device per batch), decode_tuned_gbs = decode_lanes set by hand"
+
+    # ---- BASELINE configs[3]: one stream, N GPUs, NCCL scatter / gather ------------------------------------------------
+    if not args.no_stream:
+        st = stream_section(ctx, args, rank, world, dev)
+        if st is not None:
+            extras["stream"] = st
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- rank 0, N=1 extras: entropy sweep (config 5), HC (config 3), CPU baseline -----------------------------------
-    extras = {}
-    del work
-    torch.cuda.empty_cache()
-    if world == 1 and not args.no_sweep:
-        sweep = {}
-        for cls in ("E0", "E50", "E100", "ETEXT"):
-            ctx.set_option("decode_lanes", lanes_for(cls))
-            w = Workload(ctx, min(args.sweep_blocks, args.blocks), cls, args.wave, seed=2)
-            cs = w.verify()
-            te, td = measure_pair(w, 3, 2)
-            rb = w.n * BLOCK
-            sweep[cls] = {"ratio": round(cs / rb, 4), "encode_gbs": round(rb / te / GB, 1), "decode_gbs": round(rb / td / GB, 1),
-                          "decode_roofline_frac": round((rb + cs) / td / GB / peak_hbm, 4),
-                          "encode_roofline_frac": round((rb + cs) / te / GB / peak_hbm, 4), "blocks": w.n,
-                          "decode_lanes": lanes_for(cls)}
-            del w; torch.cuda.empty_cache()
-        extras["entropy_sweep"] = sweep
+    # ---- rank 0, N=1 extras: HC (config 3), CPU baseline ---------------------------------------------------------------
     if world == 1 and not args.no_hc:
         hc = {}
         for cls in ("E50", "ETEXT"):
@@ -466,7 +644,7 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": f"{args.blocks} x 64KiB independent blocks per GPU, class {args.cls} (BASELINE configs[1]): one fast-encode launch + {nw} known-size decode launches per step",
                    "block_size": BLOCK, "class": args.cls, "blocks_per_gpu": args.blocks, "ratio": round(csum_all / total_raw, 4),
-                   "decode_lanes": lanes_for(args.cls),
+                   "decode_lanes": args.lanes or "library default: picked per batch on the device from the compression ratio",
                    "decode_wave_blocks": work_wave(args), "l2": "inputs (64 GiB raw + slots per GPU) are far larger than the 126 MB L2; no flush needed",
                    "parallelism": f"independent blocks sharded over {world} GPU(s), no data-path collective", "gb": "1e9 bytes"},
         "encode_gbs": round(enc_gbs, 2), "decode_gbs": round(dec_gbs, 2),

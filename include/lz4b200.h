@@ -121,6 +121,21 @@ int lz4b200_wrap(lz4b200_ctx* ctx, const void* src, int32_t n, int high_compress
 int lz4b200_unwrap_size(const void* src, int32_t n);
 int lz4b200_unwrap(lz4b200_ctx* ctx, const void* src, int32_t n, void* dst, int32_t dst_cap);
 
+/* The same for n packets at once: ONE encode / decode batch instead of one H2D + launch + D2H per packet.  Packet i is
+ * byte for byte what lz4b200_wrap makes of input i.  wrap_batch: dst_cap[i] >= src_len[i] + 8; out_len[i] = packet size.
+ * unwrap_batch: dst_cap[i] >= lz4b200_unwrap_size(packet i); out_len[i] = bytes restored or a negative status. */
+int lz4b200_wrap_batch(lz4b200_ctx* ctx, const void* src, const int64_t* src_off, const int32_t* src_len, int high_compression,
+                       void* dst, const int64_t* dst_off, const int32_t* dst_cap, int32_t* out_len, int32_t n);
+int lz4b200_unwrap_batch(lz4b200_ctx* ctx, const void* src, const int64_t* src_off, const int32_t* src_len,
+                         void* dst, const int64_t* dst_off, const int32_t* dst_cap, int32_t* out_len, int32_t n);
+
+/* ---- host buffers the caller keeps for a while (a pinned byte[] behind a GCHandle, a native arena) --------------------
+ * Host-memory batches copy straight from / to the caller's buffers.  From pageable memory the driver stages every copy
+ * through its own pinned bounce buffers, synchronously; page-locking a long-lived buffer once (cudaHostRegister) lets the
+ * same calls run at the full pipelined rate.  Optional: everything works without it. */
+int lz4b200_host_register(void* ptr, int64_t bytes);
+int lz4b200_host_unregister(void* ptr);
+
 /* ---- synthetic workload generator (bench/test utility; device memory) ----------------------------------------
  * Fills n_blocks * block_size bytes at dst with entropy class cls (0 E0, 1 E50, 2 E100, 3 ETEXT), block index
  * first_block + i, exactly as lz4net_b200/synth.py defines them. */
@@ -128,9 +143,11 @@ int lz4b200_synth_fill(lz4b200_ctx* ctx, void* dst, int64_t n_blocks, int32_t bl
                        int64_t first_block, void* stream);
 
 /* Tuning knobs (bench / profiling only).  key: "decode_lanes" (4|8|16|32 lanes per block, +100 = the output-staged
- * variant), "decode_lanes_auto" (host batches pick the group size from the compression ratio), "encode_ctas_per_sm"
- * (encoder warps = blocks in flight per SM, 0 = as many as shared memory allows: 14), "encode_variant" (1 = always
- * exact same-hash votes, 2 = resolved through the table: default; +10 = L2 residency hints: input evict-last, emitted output evict-first -- measured neutral),
+ * variant; 1 | 2 = the lane-per-block decoder with a 512- / 256-byte output window), "decode_lanes_auto" (the decoder is
+ * picked per batch from the compression ratio: the default), "encode_ctas_per_sm" (warp-per-block encoder warps = blocks in
+ * flight per SM, 0 = as many as shared memory allows: 14), "encode_lane_warp" (the lane-per-block encoder warp next to
+ * them: 0 off, 1 for large batches: default, 2 always), "encode_variant" (1 = always exact same-hash votes, 2 = resolved
+ * through the table: default),
  * "encode_prefetch" (bytes of input kept prefetched ahead of the parse; 0 off, < 0 L2 only), "encode_lane_copy_max" /
  * "encode_probe_max" / "encode_wide_min" (path-selection heuristics of the fast encoder, lz4_encode.cuh EncTune: they
  * never change the emitted bytes), "hc_concurrency" (blocks

@@ -310,6 +310,44 @@ class LZ4Codec:
         return dst[:r].tobytes()
 
 
+def wrap_batch(inputs, hc=False, ctx=None):
+    """n packets in ONE encode batch (lz4b200_wrap_batch): packet i == LZ4Codec.Wrap / WrapHC of inputs[i]
+    (src/LZ4/LZ4Codec.cs:510-543).  Returns a list of bytes."""
+    ctx = ctx or default_context()
+    n = len(inputs)
+    lens = np.array([len(b) for b in inputs], np.int32)
+    caps = lens + 8
+    so = np.concatenate([[0], np.cumsum(lens, dtype=np.int64)[:-1]]).astype(np.int64) if n else np.zeros(0, np.int64)
+    do = np.concatenate([[0], np.cumsum(caps, dtype=np.int64)[:-1]]).astype(np.int64) if n else np.zeros(0, np.int64)
+    src = np.frombuffer(b"".join(bytes(b) for b in inputs) + b"\0" * 16, np.uint8)
+    dst = np.zeros(int(caps.sum()) + 16, np.uint8)
+    out = np.zeros(n, np.int32)
+    native.check(native.lib().lz4b200_wrap_batch(ctx.handle, src.ctypes.data, so.ctypes.data, lens.ctypes.data, int(hc),
+                                                 dst.ctypes.data, do.ctypes.data, caps.ctypes.data, out.ctypes.data, n), "wrap_batch")
+    return [dst[int(o):int(o) + int(r)].tobytes() for o, r in zip(do, out)]
+
+
+def unwrap_batch(packets, ctx=None):
+    """Mirror image (lz4b200_unwrap_batch, src/LZ4/LZ4Codec.cs:574-599).  Raises ValueError on a corrupt packet."""
+    ctx = ctx or default_context()
+    n = len(packets)
+    l = native.lib()
+    lens = np.array([len(b) for b in packets], np.int32)
+    so = np.concatenate([[0], np.cumsum(lens, dtype=np.int64)[:-1]]).astype(np.int64) if n else np.zeros(0, np.int64)
+    src = np.frombuffer(b"".join(bytes(b) for b in packets) + b"\0" * 16, np.uint8)
+    sizes = np.array([l.lz4b200_unwrap_size(src.ctypes.data + int(o), int(k)) for o, k in zip(so, lens)], np.int32)
+    if (sizes < 0).any():
+        raise ValueError("inputBuffer size is invalid or has been corrupted")
+    do = np.concatenate([[0], np.cumsum(sizes, dtype=np.int64)[:-1]]).astype(np.int64) if n else np.zeros(0, np.int64)
+    dst = np.zeros(int(sizes.sum()) + 16, np.uint8)
+    out = np.zeros(n, np.int32)
+    native.check(l.lz4b200_unwrap_batch(ctx.handle, src.ctypes.data, so.ctypes.data, lens.ctypes.data, dst.ctypes.data,
+                                        do.ctypes.data, sizes.ctypes.data, out.ctypes.data, n), "unwrap_batch")
+    if (out < 0).any():
+        raise ValueError("LZ4 block is corrupted, or invalid length has been given.")
+    return [dst[int(o):int(o) + int(r)].tobytes() for o, r in zip(do, out)]
+
+
 class LZ4StreamMode:
     Compress, Decompress = 0, 1                                       # src/LZ4/LZ4StreamMode.cs
 

@@ -92,7 +92,7 @@ struct lz4b200_ctx {
     int64_t launches = 0;
     std::mutex mu;
 
-    uint32_t* counter() { uint32_t* c = counters + next_counter; next_counter = (next_counter + 1) % NCOUNTER; return c; }
+    uint32_t* counter() { uint32_t* c = counters + next_counter; next_counter = (next_counter + 2) % NCOUNTER; return c; }   // pairs: [block counter, decoder pick]
 };
 
 namespace {
@@ -106,11 +106,11 @@ struct DeviceGuard {
 // Decode group size from the ratio compressed/raw of a batch (tools/sweep.py): incompressible data is long literal runs
 // (whole warps, 128-bit copies), nearly-empty streams are long matches, everything between is sequence-dense (the
 // denser, the smaller the group: 8 lanes around ratio 0.58, 4 lanes around 0.37; both output-staged).
-int lanes_for_ratio(double ratio, int64_t n_blocks) { (void)n_blocks; return ratio > 0.95 ? 32 : (ratio < 0.05 ? 16 : (ratio < 0.45 ? 104 : 108)); }
+int lanes_for_ratio(double ratio, int64_t n_blocks) { (void)n_blocks; return decode_lanes_for_ratio(ratio); }
 
 int run_device(lz4b200_ctx* c, const BatchArgs& a, int op /*0 enc fast, 1 enc hc, 2 dec known, 3 dec unknown*/, cudaStream_t st, int lanes = 0)
 {
-    if (!lanes) lanes = c->decode_lanes;
+    if (!lanes && !c->decode_lanes_auto) lanes = c->decode_lanes;       // (0 = auto: the decoder is picked on the device)
     cudaError_t e = cudaSuccess;
     switch (op) {
     case 0: {
@@ -564,6 +564,19 @@ int lz4b200_set_option(lz4b200_ctx* c, const char* key, int64_t value)
 }
 
 int64_t lz4b200_launch_count(lz4b200_ctx* c) { return c ? c->launches : 0; }
+
+int lz4b200_host_register(void* ptr, int64_t bytes)
+{
+    if (!ptr || bytes <= 0) return fail(LZ4B200_E_ARG, "bad argument");
+    CU(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable));
+    return LZ4B200_OK;
+}
+int lz4b200_host_unregister(void* ptr)
+{
+    if (!ptr) return fail(LZ4B200_E_ARG, "bad argument");
+    CU(cudaHostUnregister(ptr));
+    return LZ4B200_OK;
+}
 
 int lz4b200_compress_limitedOutput(const char* s, char* d, int isize, int cap) { return single(s, d, isize, cap, 0); }
 int lz4b200_compressHC_limitedOutput(const char* s, char* d, int isize, int cap) { return single(s, d, isize, cap, 1); }

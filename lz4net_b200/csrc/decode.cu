@@ -5,6 +5,9 @@
 
 namespace lz4b200 {
 
+int decode_lanes_for_ratio(double ratio);        // (host + device: below)
+__host__ __device__ int decode_lanes_for_ratio(double ratio) { return ratio > 0.95 ? 32 : (ratio < 0.05 ? 16 : (ratio < 0.45 ? 104 : 108)); }
+
 constexpr int DEC_THREADS = 128;
 // registers: a cap of 40 (12 CTAs/SM) spills the loop state of the sub-warp variants to local memory (measured:
 // 2 LDL per sequence, half of them L1 misses) -- leave the compiler its ~56 registers, 9 CTAs = 36 warps per SM.
@@ -14,8 +17,10 @@ constexpr int DEC_MIN_CTAS = 9;
 // (the staged sub-warp variants are limited to 8 CTAs per SM by shared memory anyway: let them have 64 registers)
 template <int G, bool KNOWN, bool STAGED>
 __global__ void __launch_bounds__(DEC_THREADS, (STAGED && G < 32) ? 8 : DEC_MIN_CTAS)
-lz4_decode_kernel(BatchArgs a, uint32_t* counter)
+lz4_decode_kernel(BatchArgs a, uint32_t* counter, const int* pick, int code)
 {
+    // auto-selected launches: every candidate kernel is enqueued, the one the pick kernel chose runs, the others leave at once
+    if (pick && *pick != code) return;
     constexpr int GROUPS = DEC_THREADS / G;
     __shared__ DecRing<G> rings[GROUPS];
     __shared__ DecStage<G> stages[STAGED ? GROUPS : 1];
@@ -45,8 +50,29 @@ lz4_decode_kernel(BatchArgs a, uint32_t* counter)
     }
 }
 
+// Decoder choice for a device-memory batch, made ON the device (the call stays asynchronous): compressed / raw bytes over
+// the first blocks of the batch -> the same rule as lanes_for_ratio() on the host (capi.cu, tools/sweep.py): incompressible
+// data is long literal runs (whole warps, 128-bit copies), nearly-empty streams are long matches, everything between is
+// sequence-dense (the denser, the smaller the group; both output-staged).
+__global__ void __launch_bounds__(256) lz4_decode_pick_kernel(const int32_t* src_len, const int32_t* dst_cap, int32_t n, int* pick)
+{
+    __shared__ unsigned long long sc[8], sr[8];
+    unsigned long long c = 0, r = 0;
+    const int m = n < 8192 ? n : 8192;
+    for (int i = threadIdx.x; i < m; i += 256) { c += (unsigned)(src_len[i] > 0 ? src_len[i] : 0); r += (unsigned)(dst_cap[i] > 0 ? dst_cap[i] : 0); }
+    for (int d = 16; d > 0; d >>= 1) { c += __shfl_down_sync(0xFFFFFFFFu, c, d); r += __shfl_down_sync(0xFFFFFFFFu, r, d); }
+    if ((threadIdx.x & 31) == 0) { sc[threadIdx.x >> 5] = c; sr[threadIdx.x >> 5] = r; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        c = r = 0;
+        for (int i = 0; i < 8; i++) { c += sc[i]; r += sr[i]; }
+        const double ratio = r ? (double)c / (double)r : 1.0;
+        *pick = decode_lanes_for_ratio(ratio);
+    }
+}
+
 template <int G, bool KNOWN, bool STAGED>
-static cudaError_t launch_one(const BatchArgs& a, uint32_t* counter, const DeviceInfo& dev, cudaStream_t stream)
+static cudaError_t launch_one(const BatchArgs& a, uint32_t* counter, const DeviceInfo& dev, cudaStream_t stream, const int* pick = nullptr, int code = 0)
 {
     int per_sm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lz4_decode_kernel<G, KNOWN, STAGED>, DEC_THREADS, 0);
@@ -57,15 +83,16 @@ static cudaError_t launch_one(const BatchArgs& a, uint32_t* counter, const Devic
     long long grid = (long long)dev.num_sms * per_sm;
     if (grid > want) grid = want;
     if (grid < 1) grid = 1;
-    lz4_decode_kernel<G, KNOWN, STAGED><<<(unsigned)grid, DEC_THREADS, 0, stream>>>(a, counter);
+    lz4_decode_kernel<G, KNOWN, STAGED><<<(unsigned)grid, DEC_THREADS, 0, stream>>>(a, counter, pick, code);
     return cudaGetLastError();
 }
 
 template <int G>
-static cudaError_t launch_g(const BatchArgs& a, bool known, bool staged, uint32_t* counter, const DeviceInfo& dev, cudaStream_t stream)
+static cudaError_t launch_g(const BatchArgs& a, bool known, bool staged, uint32_t* counter, const DeviceInfo& dev, cudaStream_t stream,
+                            const int* pick = nullptr, int code = 0)
 {
-    if (staged) return known ? launch_one<G, true, true>(a, counter, dev, stream) : launch_one<G, false, true>(a, counter, dev, stream);
-    return known ? launch_one<G, true, false>(a, counter, dev, stream) : launch_one<G, false, false>(a, counter, dev, stream);
+    if (staged) return known ? launch_one<G, true, true>(a, counter, dev, stream, pick, code) : launch_one<G, false, true>(a, counter, dev, stream, pick, code);
+    return known ? launch_one<G, true, false>(a, counter, dev, stream, pick, code) : launch_one<G, false, false>(a, counter, dev, stream, pick, code);
 }
 
 // ---- lane-per-block decoder (lz4_decode_lpb.cuh): one CTA per SM, as many warps as shared memory holds rings for --------
@@ -107,6 +134,17 @@ cudaError_t launch_decode(const BatchArgs& a, bool known_len, int lanes, uint32_
     cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), stream);
     if (e != cudaSuccess) return e;
     if (launches) ++*launches;
+    if (lanes == 0) {
+        // auto: pick on the device, enqueue the four candidates (three of them return at once: ~3 us of GPU time each)
+        int* pick = (int*)(counter + 1);             // (the context hands out counters in pairs: [block counter, pick])
+        lz4_decode_pick_kernel<<<1, 256, 0, stream>>>(a.src_len, a.dst_cap, a.n_blocks, pick);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if (launches) *launches += 4;
+        if ((e = launch_g<32>(a, known_len, false, counter, dev, stream, pick, 32)) != cudaSuccess) return e;
+        if ((e = launch_g<16>(a, known_len, false, counter, dev, stream, pick, 16)) != cudaSuccess) return e;
+        if ((e = launch_g<8>(a, known_len, true, counter, dev, stream, pick, 108)) != cudaSuccess) return e;
+        return launch_g<4>(a, known_len, true, counter, dev, stream, pick, 104);
+    }
     const bool staged = lanes >= 100;            // lanes = 100 + G selects the output-staged variant
     switch (lanes % 100) {
     case 1:  return known_len ? launch_lpb<true, LpbGeom<256, 512>>(a, counter, dev, stream) : launch_lpb<false, LpbGeom<256, 512>>(a, counter, dev, stream);

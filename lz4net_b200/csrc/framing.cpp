@@ -192,4 +192,65 @@ int lz4b200_unwrap(lz4b200_ctx* ctx, const void* src, int32_t n, void* dst, int3
     return out == stored ? raw : LZ4B200_E_FORMAT;
 }
 
+// ---- batched Wrap / Unwrap: n packets, ONE encode / decode batch ---------------------------------
+// Packet i of the batch is exactly what lz4b200_wrap / LZ4Codec.Wrap (src/LZ4/LZ4Codec.cs:510-543) produces for input i:
+// u32le rawLen, u32le storedLen, payload (the compressed bytes, or the input itself when compression does not shrink it).
+// Inputs: src + src_off[i], src_len[i] bytes.  Packets: dst + dst_off[i], capacity dst_cap[i] >= src_len[i] + 8.
+// out_len[i] = packet size (or a negative status for that packet).
+int lz4b200_wrap_batch(lz4b200_ctx* ctx, const void* src, const int64_t* src_off, const int32_t* src_len, int high_compression,
+                       void* dst, const int64_t* dst_off, const int32_t* dst_cap, int32_t* out_len, int32_t n)
+{
+    if (!ctx || n < 0) return LZ4B200_E_ARG;
+    if (n == 0) return LZ4B200_OK;
+    if (!src || !dst || !src_off || !src_len || !dst_off || !dst_cap || !out_len) return LZ4B200_E_ARG;
+    const uint8_t* s = (const uint8_t*)src; uint8_t* d = (uint8_t*)dst;
+    auto poke4 = [](uint8_t* p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24); };
+    std::vector<int64_t> po(n); std::vector<int32_t> pc(n), res(n, 0);
+    for (int32_t i = 0; i < n; i++) {
+        if (src_len[i] < 0 || (int64_t)dst_cap[i] < (int64_t)src_len[i] + 8) return LZ4B200_E_ARG;
+        po[i] = dst_off[i] + 8; pc[i] = src_len[i];                  // payload capacity = the input length (:518-523)
+    }
+    int rc = lz4b200_encode_batch(ctx, s, src_off, src_len, d, po.data(), pc.data(), res.data(), n,
+                                  high_compression ? LZ4B200_MODE_HC : LZ4B200_MODE_FAST, LZ4B200_MEM_HOST, nullptr);
+    if (rc != LZ4B200_OK) return rc;
+    for (int32_t i = 0; i < n; i++) {
+        uint8_t* p = d + dst_off[i]; const int32_t len = src_len[i];
+        poke4(p, (uint32_t)len);
+        if (len == 0) { poke4(p + 4, 0); out_len[i] = 8; continue; }
+        if (res[i] >= len || res[i] <= 0) { poke4(p + 4, (uint32_t)len); std::memcpy(p + 8, s + src_off[i], (size_t)len); out_len[i] = len + 8; }
+        else { poke4(p + 4, (uint32_t)res[i]); out_len[i] = res[i] + 8; }
+    }
+    return LZ4B200_OK;
+}
+
+// Mirror image (src/LZ4/LZ4Codec.cs:574-599).  Packets: src + src_off[i], src_len[i] bytes.  Outputs: dst + dst_off[i],
+// capacity dst_cap[i] >= lz4b200_unwrap_size(packet i).  out_len[i] = bytes restored, or LZ4B200_E_FORMAT / E_ARG.
+int lz4b200_unwrap_batch(lz4b200_ctx* ctx, const void* src, const int64_t* src_off, const int32_t* src_len,
+                         void* dst, const int64_t* dst_off, const int32_t* dst_cap, int32_t* out_len, int32_t n)
+{
+    if (!ctx || n < 0) return LZ4B200_E_ARG;
+    if (n == 0) return LZ4B200_OK;
+    if (!src || !dst || !src_off || !src_len || !dst_off || !dst_cap || !out_len) return LZ4B200_E_ARG;
+    const uint8_t* s = (const uint8_t*)src; uint8_t* d = (uint8_t*)dst;
+    std::vector<int64_t> so, dof; std::vector<int32_t> sl, dc, res, idx;
+    for (int32_t i = 0; i < n; i++) {
+        const uint8_t* p = s + src_off[i];
+        const int size = lz4b200_unwrap_size(p, src_len[i]);
+        if (size < 0) { out_len[i] = size; continue; }
+        if (size > dst_cap[i]) { out_len[i] = LZ4B200_E_ARG; continue; }
+        const int32_t raw = (int32_t)(p[0] | p[1] << 8 | p[2] << 16 | (uint32_t)p[3] << 24);
+        const int32_t stored = (int32_t)(p[4] | p[5] << 8 | p[6] << 16 | (uint32_t)p[7] << 24);
+        if (stored >= raw) { std::memcpy(d + dst_off[i], p + 8, (size_t)stored); out_len[i] = stored; continue; }
+        so.push_back(src_off[i] + 8); sl.push_back(stored); dof.push_back(dst_off[i]); dc.push_back(raw); idx.push_back(i);
+    }
+    if (!so.empty()) {
+        res.assign(so.size(), -1);
+        int rc = lz4b200_decode_batch(ctx, s, so.data(), sl.data(), d, dof.data(), dc.data(), res.data(), (int32_t)so.size(), 1,
+                                      LZ4B200_MEM_HOST, nullptr);
+        if (rc != LZ4B200_OK) return rc;
+        for (size_t j = 0; j < so.size(); j++) out_len[idx[j]] = res[j] == sl[j] ? dc[j] : LZ4B200_E_FORMAT;
+    }
+    return LZ4B200_OK;
+}
+
 }  // extern "C"

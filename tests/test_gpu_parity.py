@@ -322,6 +322,26 @@ def test_wrap_unwrap(ctx):
         LZ4Codec.Unwrap(b"\x01\x02\x03")
 
 
+@pytest.mark.parametrize("hc", [False, True])
+def test_wrap_unwrap_batch(ctx, hc):
+    """n packets through ONE batch (lz4b200_wrap_batch / unwrap_batch): every packet is byte for byte what the per-packet
+    call and the reference rule (src/LZ4/LZ4Codec.cs:510-543: stored when compression does not shrink it) produce."""
+    from lz4net_b200 import LZ4Codec, codec
+    inputs = [cases.LOREM, cases.content("E0", 2048, 0).tobytes(), b"a", b"", cases.AUTOTEST, cases.content("ETEXT", 70000, 1).tobytes()]
+    inputs += [cases.content(m, n, seed=3 + i).tobytes() for i, m in enumerate(cases.MODELS) for n in (1, 100, 5000, 65536)]
+    packets = codec.wrap_batch(inputs, hc=hc)
+    single = LZ4Codec.WrapHC if hc else LZ4Codec.Wrap
+    for d, p in zip(inputs, packets):
+        r, o = (oracle.encode_hc if hc else oracle.encode)(d, cap=len(d)) if d else (0, b"")
+        want = bytes(8) if not d else (len(d).to_bytes(4, "little") * 2 + d if (r >= len(d) or r <= 0) else len(d).to_bytes(4, "little") + r.to_bytes(4, "little") + o)
+        assert p == want, len(d)
+    assert packets[:6] == [single(d) for d in inputs[:6]]
+    assert codec.unwrap_batch(packets) == inputs
+    bad = list(packets); bad[3] = b"\x01\x02\x03"
+    with pytest.raises(ValueError):
+        codec.unwrap_batch(bad)
+
+
 def _ref_stream(data, block_size, hc):
     """The LZ4Stream wire bytes, built from the oracle (src/LZ4/LZ4Stream.cs:225-269)."""
     def varint(v):
