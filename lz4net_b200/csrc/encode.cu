@@ -19,21 +19,27 @@ constexpr int ENC_SMEM_WARPS = 14;
 
 template <int DUP, bool LPB>
 __global__ void __launch_bounds__(32 * (ENC_SMEM_WARPS + (LPB ? 1 : 0)), 1)
-lz4_encode_fast_kernel(BatchArgs a, uint32_t* counter, EncTune tune, int warp_warps, uint8_t* arena)
+lz4_encode_fast_kernel(BatchArgs a, unsigned long long* queue, EncTune tune, int warp_warps, uint8_t* arena, uint32_t reserve)
 {
+    // queue: (blocks taken from the front) << 32 | (blocks taken from the back) -- warps take from the front, the lanes
+    // of the lane-per-block warp from the back (lz4_encode_lpb.cuh)
     extern __shared__ __align__(16) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (LPB && warp >= warp_warps) {
         const EncLpbBatch b{a.src, a.src_off, a.src_len, a.dst, a.dst_off, a.dst_cap, a.out_len, a.n_blocks};
-        lpb_encode_warp(arena + (size_t)blockIdx.x * 32 * 16384, b, counter, lane);
+        lpb_encode_warp(arena + (size_t)blockIdx.x * ENC_LPB_LANES * ENC_LPB_TABLE, b, queue, reserve, lane);
         return;
     }
     EncShared* sh = (EncShared*)smem + warp;
     for (;;) {
-        uint32_t b = 0;
-        if (lane == 0) b = atomicAdd(counter, 1u);
+        uint32_t b = 0xFFFFFFFFu;
+        if (lane == 0) {
+            const unsigned long long old = atomicAdd(queue, 1ull << 32);
+            const uint32_t f = (uint32_t)(old >> 32), taken_back = (uint32_t)old;
+            if (f < (uint32_t)a.n_blocks && f + taken_back < (uint32_t)a.n_blocks) b = f;
+        }
         b = simt::shfl(0xFFFFFFFFu, b, 0);
-        if (b >= (uint32_t)a.n_blocks) break;
+        if (b == 0xFFFFFFFFu) break;
         const int r = encode_block<DUP, 0>(sh, a.src + a.src_off[b], a.src_len[b], a.dst + a.dst_off[b], a.dst_cap[b], lane, tune);
         if (lane == 0) a.out_len[b] = r;
     }
@@ -41,15 +47,18 @@ lz4_encode_fast_kernel(BatchArgs a, uint32_t* counter, EncTune tune, int warp_wa
 
 template <int DUP, bool LPB>
 static cudaError_t launch_fast_t(const BatchArgs& a, uint32_t* counter, int dyn, long long grid, int warps, uint8_t* arena,
-                                 const EncTune& tune, cudaStream_t stream)
+                                 const EncTune& tune, cudaStream_t stream, bool forced = false)
 {
     cudaError_t e = cudaFuncSetAttribute(lz4_encode_fast_kernel<DUP, LPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
     if (e != cudaSuccess) return e;
-    lz4_encode_fast_kernel<DUP, LPB><<<(unsigned)grid, 32 * (warps + (LPB ? 1 : 0)), dyn, stream>>>(a, counter, tune, warps, arena);
+    // the lanes stop taking blocks when fewer than `reserve` are left: enough for every warp to stay busy for about one
+    // lane-block time (a lane holds a block ~8 warp-block times)
+    const uint32_t reserve = forced ? 0u : (uint32_t)(grid * warps * 8);       // (forced: tests with small batches)
+    lz4_encode_fast_kernel<DUP, LPB><<<(unsigned)grid, 32 * (warps + (LPB ? 1 : 0)), dyn, stream>>>(a, (unsigned long long*)counter, tune, warps, arena, reserve);
     return cudaGetLastError();
 }
 
-size_t encode_arena_bytes(const DeviceInfo& dev) { return (size_t)dev.num_sms * 32 * 16384; }     // one table per lane of the lane-per-block warp
+size_t encode_arena_bytes(const DeviceInfo& dev) { return (size_t)dev.num_sms * ENC_LPB_LANES * ENC_LPB_TABLE; }     // one table per block-owning lane
 
 cudaError_t launch_encode_fast(const BatchArgs& a, uint32_t* counter, int warps_per_sm, int lane_warp, const int* tune4, int variant,
                                void* arena, const DeviceInfo& dev, cudaStream_t stream, int64_t* launches)
@@ -64,21 +73,21 @@ cudaError_t launch_encode_fast(const BatchArgs& a, uint32_t* counter, int warps_
     long long grid = dev.num_sms;
     int warps = warps_per_sm;
     bool lpb = lane_warp != 0 && arena != nullptr;
-    if (lane_warp == 1 && a.n_blocks < (long long)dev.num_sms * (warps + 32) * 8) lpb = false;    // (lane_warp == 2 forces it: tests)
+    if (lane_warp == 1 && a.n_blocks < (long long)dev.num_sms * warps * 32) lpb = false;    // (lane_warp == 2 forces it: tests)
     if (a.n_blocks < (long long)dev.num_sms * warps) {
         warps = (int)((a.n_blocks + dev.num_sms - 1) / dev.num_sms);
         grid = (a.n_blocks + warps - 1) / warps;
     }
     const int dyn = warps * (int)sizeof(EncShared);
-    cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), stream);
+    cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream);      // (the context hands out counters in 8-byte pairs)
     if (e != cudaSuccess) return e;
     if (launches) ++*launches;
     EncTune tune; tune.pf_dist = tune4[0]; tune.lane_copy_max = tune4[1]; tune.probe_max = tune4[2]; tune.wide_min = tune4[3];
     uint8_t* ar = (uint8_t*)arena;
     // variant: how same-hash iterations of one round are found by the warp-per-block encoders (lz4_encode.cuh):
     // 1 = always exact (one vote per hash bit), 2 = through the table, pairs resolved in place
-    if (lpb) return variant == 1 ? launch_fast_t<1, true>(a, counter, dyn, grid, warps, ar, tune, stream)
-                                 : launch_fast_t<2, true>(a, counter, dyn, grid, warps, ar, tune, stream);
+    if (lpb) return variant == 1 ? launch_fast_t<1, true>(a, counter, dyn, grid, warps, ar, tune, stream, lane_warp == 2)
+                                 : launch_fast_t<2, true>(a, counter, dyn, grid, warps, ar, tune, stream, lane_warp == 2);
     return variant == 1 ? launch_fast_t<1, false>(a, counter, dyn, grid, warps, ar, tune, stream)
                         : launch_fast_t<2, false>(a, counter, dyn, grid, warps, ar, tune, stream);
 }

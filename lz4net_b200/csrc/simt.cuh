@@ -77,6 +77,10 @@ SIMT_DEV void sts_u32(smem_ref r, uint32_t off, uint32_t v) { asm volatile("st.s
 SIMT_DEV uint32_t ldt_hint_u16(const void* p, uint64_t pol) { uint16_t v; asm volatile("ld.global.L2::cache_hint.u16 %0, [%1], %2;" : "=h"(v) : "l"(p), "l"(pol) : "memory"); return v; }
 SIMT_DEV uint32_t ldt_hint_u32(const void* p, uint64_t pol) { uint32_t v; asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol) : "memory"); return v; }
 SIMT_DEV void stt_hint_u16(void* p, uint32_t v, uint64_t pol) { asm volatile("st.global.L2::cache_hint.u16 [%0], %1, %2;" :: "l"(p), "h"((uint16_t)v), "l"(pol) : "memory"); }
+SIMT_DEV uint2 ldt_hint_v2(const void* p, uint64_t pol) { uint2 v; asm volatile("ld.global.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol) : "memory"); return v; }
+SIMT_DEV void stt_hint_v2(void* p, uint2 v, uint64_t pol) { asm volatile("st.global.L2::cache_hint.v2.u32 [%0], {%1,%2}, %3;" :: "l"(p), "r"(v.x), "r"(v.y), "l"(pol) : "memory"); }
+SIMT_DEV unsigned long long atomic_load_u64(unsigned long long* p) { return *(volatile unsigned long long*)p; }
+SIMT_DEV unsigned long long atomic_cas_u64(unsigned long long* p, unsigned long long cmp, unsigned long long val) { return atomicCAS(p, cmp, val); }
 SIMT_DEV void stt_hint_u32(void* p, uint32_t v, uint64_t pol) { asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" :: "l"(p), "r"(v), "l"(pol) : "memory"); }
 
 // Ampere-style asynchronous copy, 16 bytes global -> shared per lane (both addresses 16-byte aligned), tracked per thread:

@@ -122,8 +122,8 @@ void emu_decode_lpb(int geo, int known, int nblocks, const uint8_t* const* src, 
 }
 
 // lane-per-block encoder: the whole warp loop, blocks handed out through the counter
-struct EncLpbJob { EncLpbBatch a; uint32_t counter; uint8_t* tables; };
-void enc_lpb_entry(int lane, void* arg) { EncLpbJob* j = (EncLpbJob*)arg; lpb_encode_warp(j->tables, j->a, &j->counter, lane); }
+struct EncLpbJob { EncLpbBatch a; unsigned long long queue; uint8_t* tables; };
+void enc_lpb_entry(int lane, void* arg) { EncLpbJob* j = (EncLpbJob*)arg; lpb_encode_warp(j->tables, j->a, &j->queue, 0u, lane); }
 
 void emu_encode_lpb(int nblocks, const uint8_t* const* src, const int* n, uint8_t* const* dst, const int* cap,
                     int* result, uint64_t sched_seed)
@@ -133,9 +133,9 @@ void emu_encode_lpb(int nblocks, const uint8_t* const* src, const int* n, uint8_
     for (int i = 0; i < nblocks; i++) { so[i] = src[i] - sb; dof[i] = dst[i] - db; }
     EncLpbJob j;
     j.a = EncLpbBatch{sb, so.data(), n, db, dof.data(), cap, result, nblocks};
-    j.counter = 0;
-    j.tables = (uint8_t*)aligned_alloc(128, 32 * 16384);
-    memset(j.tables, 0x5A, 32 * 16384);                 // stale garbage, like a reused arena
+    j.queue = 0;
+    j.tables = (uint8_t*)aligned_alloc(128, ENC_LPB_LANES * ENC_LPB_TABLE);
+    memset(j.tables, 0x5A, ENC_LPB_LANES * ENC_LPB_TABLE);     // stale garbage, like a reused arena
     simt_emu::run_warp(enc_lpb_entry, &j, sched_seed);
     free(j.tables);
 }

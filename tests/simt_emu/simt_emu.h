@@ -67,6 +67,10 @@ static inline uint32_t ldt_hint_u16(const void* p, uint64_t) { return ldt_u16(p)
 static inline uint32_t ldt_hint_u32(const void* p, uint64_t) { return ldt_u32(p); }
 static inline void stt_hint_u16(void* p, uint32_t v, uint64_t) { uint16_t t = (uint16_t)v; memcpy(p, &t, 2); }
 static inline void stt_hint_u32(void* p, uint32_t v, uint64_t) { memcpy(p, &v, 4); }
+static inline uint2 ldt_hint_v2(const void* p, uint64_t) { uint2 v; memcpy(&v, p, 8); return v; }
+static inline void stt_hint_v2(void* p, uint2 v, uint64_t) { memcpy(p, &v, 8); }
+static inline unsigned long long atomic_load_u64(unsigned long long* p) { return *p; }
+static inline unsigned long long atomic_cas_u64(unsigned long long* p, unsigned long long cmp, unsigned long long val) { unsigned long long o = *p; if (o == cmp) *p = val; return o; }
 // cp.async: the copy is DEFERRED until the wait that covers its group (per lane), so that code which reads a unit before
 // waiting for it, or overwrites a ring slot that is still to be read, fails in the emulator as well
 void cp_async16_emu(void* sdst, const void* gsrc);
