@@ -34,17 +34,20 @@
 
 namespace lz4b200 {
 
-template <int IN_, int OUT_>
+// DEPTH: how many iterations ahead the input is requested (1: a unit is waited for one full iteration after its request,
+// needs IN >= 3 LOOK + 16; 0: requests are waited for at the top of the next iteration, IN >= 2 LOOK + 16 -- the smaller
+// rings let more warps share an SM, which is what hides the latency then).
+template <int IN_, int OUT_, int MAXRUN_ = 64, int DEPTH_ = 1>
 struct LpbGeom {
-    static constexpr int IN = IN_, OUT = OUT_;
+    static constexpr int IN = IN_, OUT = OUT_, DEPTH = DEPTH_;
     static constexpr int IN_STRIDE = IN + 16;                      // == 16 (mod 128): the 128-bit fills of the eight lanes of a phase never collide
-    static constexpr int MAXL = 64, MAXM = 64;                     // longest literal run / match a lane copies by itself
+    static constexpr int MAXL = MAXRUN_, MAXM = MAXRUN_;           // longest literal run / match a lane copies by itself
     static constexpr int LOOK = 1 + 1 + MAXL + 2 + 1 + 4;          // stream bytes such a sequence can touch (+ word over-read)
     static constexpr int WIN = OUT - 8;                            // matches up to this far back are served by the output ring
     static constexpr int CHUNK = 128;                              // flush unit (bytes, aligned in the output buffer)
     static constexpr int HIGH = OUT - 256 > CHUNK ? OUT - 256 : CHUNK;   // a lane with this many unflushed bytes forces a flush step
     static_assert((IN & (IN - 1)) == 0 && (OUT & (OUT - 1)) == 0 && OUT >= 256, "ring sizes");
-    static_assert(IN >= 3 * LOOK + 16 && HIGH + MAXL + MAXM <= OUT, "ring capacity");
+    static_assert(IN >= (2 + DEPTH) * LOOK + 16 && HIGH + MAXL + MAXM <= OUT, "ring capacity");
 };
 
 template <class GEO> struct alignas(128) LpbShared {
@@ -216,7 +219,7 @@ SIMT_DEV void lpb_decode_warp(LpbShared<GEO>* sh, const LpbBatch& a, uint32_t* c
         if (!simt::ballot(FULL, active)) break;
         // everything requested up to the last commit but one has landed; a fresh block waits for its first units
         simt::cp_async_commit();
-        if (simt::ballot(FULL, fresh)) { simt::cp_async_wait<0>(); f1 = iland = ifill; }
+        if (GEO::DEPTH == 0 || simt::ballot(FULL, fresh)) { simt::cp_async_wait<0>(); f1 = iland = ifill; }
         else { simt::cp_async_wait<1>(); iland = f1; f1 = ifill; }  // (all groups but the one just committed are complete: everything below the previous commit's ifill)
         fresh = false;
 
