@@ -144,9 +144,8 @@ int lz4b200_synth_fill(lz4b200_ctx* ctx, void* dst, int64_t n_blocks, int32_t bl
 
 /* Tuning knobs (bench / profiling only).  key: "decode_lanes" (4|8|16|32 lanes per block, +100 = the output-staged
  * variant; 1 | 2 = the lane-per-block decoder with a 512- / 256-byte output window), "decode_lanes_auto" (the decoder is
- * picked per batch from the compression ratio: the default), "encode_ctas_per_sm" (warp-per-block encoder warps = blocks in
- * flight per SM, 0 = as many as shared memory allows: 14), "encode_lane_warp" (the lane-per-block encoder warp next to
- * them: 0 off, 1 for large batches: default, 2 always), "encode_variant" (1 = always exact same-hash votes, 2 = resolved
+ * picked per batch from the compression ratio: the default), "encode_ctas_per_sm" (encoder warps = blocks in
+ * flight per SM, 0 = as many as shared memory allows: 14), "encode_variant" (1 = always exact same-hash votes, 2 = resolved
  * through the table: default),
  * "encode_prefetch" (bytes of input kept prefetched ahead of the parse; 0 off, < 0 L2 only), "encode_lane_copy_max" /
  * "encode_probe_max" / "encode_wide_min" (path-selection heuristics of the fast encoder, lz4_encode.cuh EncTune: they

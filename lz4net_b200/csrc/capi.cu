@@ -77,13 +77,12 @@ struct lz4b200_ctx {
     cudaStream_t stream = nullptr;
     uint32_t* counters = nullptr;
     int next_counter = 0;
-    DevBuf hc_arena, compact_tmp, enc_arena;
+    DevBuf hc_arena, compact_tmp;
     cudaEvent_t hc_done = nullptr;         // the HC state arena is shared: HC launches are chained through this event
     cudaEvent_t compact_done = nullptr;    // likewise the scan scratch of lz4b200_compact
     int decode_lanes = 16;                 // lanes per block for device-memory batches (+100 = output-staged variant)
     bool decode_lanes_auto = true;         // host-memory batches: chosen per chunk from the compression ratio
-    int encode_ctas_per_sm = 0;            // warp-per-block encoder warps per SM: 0 = as many as shared memory holds tables for (14)
-    int encode_lane_warp = 1;              // the lane-per-block encoder warp next to them: 0 off, 1 for large batches (default), 2 always
+    int encode_ctas_per_sm = 0;            // encoder warps (= blocks in flight) per SM: 0 = as many as shared memory holds tables for (14)
     int encode_variant = 2;                // same-hash detection inside a round: 1 exact votes, 2 optimistic (default)
     int encode_tune[4] = {512, 12, 8, 24}; // prefetch distance, lane_copy_max, probe_max, wide_min (lz4_encode.cuh EncTune)
     size_t host_chunk_bytes = HOST_CHUNK_BYTES_DEFAULT;
@@ -113,17 +112,7 @@ int run_device(lz4b200_ctx* c, const BatchArgs& a, int op /*0 enc fast, 1 enc hc
     if (!lanes && !c->decode_lanes_auto) lanes = c->decode_lanes;       // (0 = auto: the decoder is picked on the device)
     cudaError_t e = cudaSuccess;
     switch (op) {
-    case 0: {
-        // (the lane-per-block warp's table arena is written by every launch: launches on different streams of one context
-        // are serialised on it through the same event as the HC arena)
-        const bool lw = c->encode_lane_warp != 0;
-        if (lw && !c->enc_arena.p) { CU(cudaDeviceSynchronize()); CU(c->enc_arena.reserve(encode_arena_bytes(c->dev))); }
-        if (lw) CU(cudaStreamWaitEvent(st, c->hc_done, 0));
-        e = launch_encode_fast(a, c->counter(), c->encode_ctas_per_sm, c->encode_lane_warp, c->encode_tune, c->encode_variant,
-                               lw ? c->enc_arena.p : nullptr, c->dev, st, &c->launches);
-        if (lw && e == cudaSuccess) e = cudaEventRecord(c->hc_done, st);
-        break;
-    }
+    case 0: e = launch_encode_fast(a, c->counter(), c->encode_ctas_per_sm, c->encode_tune, c->encode_variant, c->dev, st, &c->launches); break;
     case 1: {
         const int conc = (int)std::min<int64_t>(c->hc_concurrency, std::max(a.n_blocks, 1));
         const size_t need = hc_scratch_bytes(conc);
@@ -455,7 +444,7 @@ void lz4b200_destroy(lz4b200_ctx* c)
         if (s.done) cudaEventDestroy(s.done);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
-    c->hc_arena.release(); c->compact_tmp.release(); c->enc_arena.release();
+    c->hc_arena.release(); c->compact_tmp.release();
     if (c->hc_done) cudaEventDestroy(c->hc_done);
     if (c->compact_done) cudaEventDestroy(c->compact_done);
     if (c->counters) cudaFree(c->counters);
@@ -549,7 +538,6 @@ int lz4b200_set_option(lz4b200_ctx* c, const char* key, int64_t value)
         if (value < 0 || value > 65536) return fail(LZ4B200_E_ARG, "encoder heuristic out of range");
         c->encode_tune[k == "encode_lane_copy_max" ? 1 : (k == "encode_probe_max" ? 2 : 3)] = (int)value;
     }
-    else if (k == "encode_lane_warp") { if (value < 0 || value > 2) return fail(LZ4B200_E_ARG, "encode_lane_warp must be 0, 1 or 2"); c->encode_lane_warp = (int)value; }
     else if (k == "encode_ctas_per_sm") { if (value < 0 || value > 32) return fail(LZ4B200_E_ARG, "encode_ctas_per_sm out of range"); c->encode_ctas_per_sm = (int)value; }
     else if (k == "hc_concurrency") {
         if (value < 32 || value > (1 << 20)) return fail(LZ4B200_E_ARG, "hc_concurrency out of range");

@@ -20,11 +20,8 @@ struct DeviceInfo { int num_sms; int smem_per_sm; int smem_optin; };
 int         decode_lanes_for_ratio(double ratio);
 cudaError_t launch_decode(const BatchArgs& a, bool known_len, int lanes_per_block, uint32_t* counter,
                           const DeviceInfo& dev, cudaStream_t stream, int64_t* launches);
-cudaError_t launch_encode_fast(const BatchArgs& a, uint32_t* counter, int warps_per_sm, int lane_warp /* 0 off, 1 on for large batches, 2 always */,
-                               const int* tune4 /* prefetch, lane_copy_max, probe_max, wide_min */, int variant,
-                               void* arena /* encode_arena_bytes() of global memory for the lane-per-block warp's tables; null = no such warp */,
+cudaError_t launch_encode_fast(const BatchArgs& a, uint32_t* counter, int warps_per_sm, const int* tune4 /* prefetch, lane_copy_max, probe_max, wide_min */, int variant,
                                const DeviceInfo& dev, cudaStream_t stream, int64_t* launches);
-size_t      encode_arena_bytes(const DeviceInfo& dev);
 size_t      hc_scratch_bytes(int concurrency);
 cudaError_t launch_encode_hc(const BatchArgs& a, void* scratch, int concurrency, uint32_t* counter,
                              const DeviceInfo& dev, cudaStream_t stream, int64_t* launches);

@@ -27,6 +27,7 @@ SIMT_DEV int ffs(uint32_t v) { return __ffs((int)v); }
 SIMT_DEV int clz(uint32_t v) { return __clz((int)v); }
 SIMT_DEV int popc(uint32_t v) { return __popc(v); }
 SIMT_DEV uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) { return __funnelshift_r(lo, hi, sh); }
+SIMT_DEV uint32_t funnel_rc(uint32_t lo, uint32_t hi, uint32_t sh) { return __funnelshift_rc(lo, hi, sh); }   // shift clamped to 32 (-> hi)
 SIMT_DEV uint32_t funnel_l(uint32_t lo, uint32_t hi, uint32_t sh) { return __funnelshift_l(lo, hi, sh); }     // high word of (hi:lo) << sh
 
 // Opaque identity: stops the compiler from re-deriving a value from its parts at every use (e.g. a 64-bit pointer
@@ -70,18 +71,6 @@ SIMT_DEV uint4 lds_v4(smem_ref r, uint32_t off) { uint4 v; asm volatile("ld.shar
 SIMT_DEV void sts_u8(smem_ref r, uint32_t off, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(r.a + off), "r"(v) : "memory"); }
 SIMT_DEV void sts_u16(smem_ref r, uint32_t off, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" :: "r"(r.a + off), "h"((uint16_t)v) : "memory"); }
 SIMT_DEV void sts_u32(smem_ref r, uint32_t off, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(r.a + off), "r"(v) : "memory"); }
-
-// Position-table entries kept in global memory (the lane-per-block encoder): volatile asm so the compiler keeps every
-// access in program order, with an L2 eviction-priority hint (createpolicy evict_last: the tables are the data that must
-// stay L2-resident while the blocks stream through).
-SIMT_DEV uint32_t ldt_hint_u16(const void* p, uint64_t pol) { uint16_t v; asm volatile("ld.global.L2::cache_hint.u16 %0, [%1], %2;" : "=h"(v) : "l"(p), "l"(pol) : "memory"); return v; }
-SIMT_DEV uint32_t ldt_hint_u32(const void* p, uint64_t pol) { uint32_t v; asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol) : "memory"); return v; }
-SIMT_DEV void stt_hint_u16(void* p, uint32_t v, uint64_t pol) { asm volatile("st.global.L2::cache_hint.u16 [%0], %1, %2;" :: "l"(p), "h"((uint16_t)v), "l"(pol) : "memory"); }
-SIMT_DEV uint2 ldt_hint_v2(const void* p, uint64_t pol) { uint2 v; asm volatile("ld.global.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol) : "memory"); return v; }
-SIMT_DEV void stt_hint_v2(void* p, uint2 v, uint64_t pol) { asm volatile("st.global.L2::cache_hint.v2.u32 [%0], {%1,%2}, %3;" :: "l"(p), "r"(v.x), "r"(v.y), "l"(pol) : "memory"); }
-SIMT_DEV unsigned long long atomic_load_u64(unsigned long long* p) { return *(volatile unsigned long long*)p; }
-SIMT_DEV unsigned long long atomic_cas_u64(unsigned long long* p, unsigned long long cmp, unsigned long long val) { return atomicCAS(p, cmp, val); }
-SIMT_DEV void stt_hint_u32(void* p, uint32_t v, uint64_t pol) { asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" :: "l"(p), "r"(v), "l"(pol) : "memory"); }
 
 // Ampere-style asynchronous copy, 16 bytes global -> shared per lane (both addresses 16-byte aligned), tracked per thread:
 // every lane of a warp copies for itself in ONE instruction (the bulk form, UBLKCP, takes uniform operands and would be

@@ -86,12 +86,8 @@ def encode(blocks, caps=None, sched_seed=1, src_skew=0, dst_skew=0, variant=2, t
     res = np.zeros(n, np.int32)
     sp = (C.c_void_p * n)(*[a.ctypes.data + src_skew for a in srcs])
     dp = (C.c_void_p * n)(*[a.ctypes.data + 32 + dst_skew for a in dsts])
-    if variant == 20:        # lane-per-block encoder
-        lib().emu_encode_lpb(n, sp, ns.ctypes.data_as(C.c_void_p), dp, cps.ctypes.data_as(C.c_void_p),
-                             res.ctypes.data_as(C.c_void_p), C.c_uint64(sched_seed))
-    else:
-        lib().emu_encode(n, sp, ns.ctypes.data_as(C.c_void_p), dp, cps.ctypes.data_as(C.c_void_p),
-                         res.ctypes.data_as(C.c_void_p), C.c_uint64(sched_seed))
+    lib().emu_encode(n, sp, ns.ctypes.data_as(C.c_void_p), dp, cps.ctypes.data_as(C.c_void_p),
+                     res.ctypes.data_as(C.c_void_p), C.c_uint64(sched_seed))
     outs = []
     for d, c, r in zip(dsts, caps, res.tolist()):
         lo = 32 + dst_skew

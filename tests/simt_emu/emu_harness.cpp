@@ -5,7 +5,6 @@
 #include "lz4_decode.cuh"
 #include "lz4_decode_lpb.cuh"
 #include "lz4_encode.cuh"
-#include "lz4_encode_lpb.cuh"
 #include "lz4hc_encode.cuh"
 #include <stdlib.h>
 #include <vector>
@@ -119,25 +118,6 @@ void emu_decode_lpb(int geo, int known, int nblocks, const uint8_t* const* src, 
     memset(j.sh, 0xA5, sizeof(LpbShared<LpbGeom<256, 512>>));
     simt_emu::run_warp(lpb_entry, &j, sched_seed);
     free(j.sh);
-}
-
-// lane-per-block encoder: the whole warp loop, blocks handed out through the counter
-struct EncLpbJob { EncLpbBatch a; unsigned long long queue; uint8_t* tables; };
-void enc_lpb_entry(int lane, void* arg) { EncLpbJob* j = (EncLpbJob*)arg; lpb_encode_warp(j->tables, j->a, &j->queue, 0u, lane); }
-
-void emu_encode_lpb(int nblocks, const uint8_t* const* src, const int* n, uint8_t* const* dst, const int* cap,
-                    int* result, uint64_t sched_seed)
-{
-    std::vector<int64_t> so(nblocks), dof(nblocks);
-    const uint8_t* sb = nblocks ? src[0] : nullptr; uint8_t* db = nblocks ? dst[0] : nullptr;
-    for (int i = 0; i < nblocks; i++) { so[i] = src[i] - sb; dof[i] = dst[i] - db; }
-    EncLpbJob j;
-    j.a = EncLpbBatch{sb, so.data(), n, db, dof.data(), cap, result, nblocks};
-    j.queue = 0;
-    j.tables = (uint8_t*)aligned_alloc(128, ENC_LPB_LANES * ENC_LPB_TABLE);
-    memset(j.tables, 0x5A, ENC_LPB_LANES * ENC_LPB_TABLE);     // stale garbage, like a reused arena
-    simt_emu::run_warp(enc_lpb_entry, &j, sched_seed);
-    free(j.tables);
 }
 
 // the HC encoder is one thread per block: plain scalar code, no warp needed

@@ -34,6 +34,7 @@ static inline int ffs(uint32_t v) { return __builtin_ffs((int)v); }
 static inline int clz(uint32_t v) { return v ? __builtin_clz(v) : 32; }
 static inline int popc(uint32_t v) { return __builtin_popcount(v); }
 static inline uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) { uint64_t t = ((uint64_t)hi << 32) | lo; return (uint32_t)(t >> (sh & 31)); }
+static inline uint32_t funnel_rc(uint32_t lo, uint32_t hi, uint32_t sh) { if (sh >= 32) return hi; uint64_t t = ((uint64_t)hi << 32) | lo; return (uint32_t)(t >> sh); }
 static inline uint32_t funnel_l(uint32_t lo, uint32_t hi, uint32_t sh) { uint64_t t = ((uint64_t)hi << 32) | lo; return (uint32_t)((t << (sh & 31)) >> 32); }
 
 template <class T> static inline T* keep(T* p) { return p; }
@@ -61,16 +62,6 @@ static inline uint4 lds_v4(smem_ref r, uint32_t off) { uint4 v; memcpy(&v, r.p +
 static inline void sts_u8(smem_ref r, uint32_t off, uint32_t v) { r.p[off] = (uint8_t)v; }
 static inline void sts_u16(smem_ref r, uint32_t off, uint32_t v) { uint16_t t = (uint16_t)v; memcpy(r.p + off, &t, 2); }
 static inline void sts_u32(smem_ref r, uint32_t off, uint32_t v) { memcpy(r.p + off, &v, 4); }
-static inline uint32_t ldt_u16(const void* p) { uint16_t v; memcpy(&v, p, 2); return v; }
-static inline uint32_t ldt_u32(const void* p) { uint32_t v; memcpy(&v, p, 4); return v; }
-static inline uint32_t ldt_hint_u16(const void* p, uint64_t) { return ldt_u16(p); }
-static inline uint32_t ldt_hint_u32(const void* p, uint64_t) { return ldt_u32(p); }
-static inline void stt_hint_u16(void* p, uint32_t v, uint64_t) { uint16_t t = (uint16_t)v; memcpy(p, &t, 2); }
-static inline void stt_hint_u32(void* p, uint32_t v, uint64_t) { memcpy(p, &v, 4); }
-static inline uint2 ldt_hint_v2(const void* p, uint64_t) { uint2 v; memcpy(&v, p, 8); return v; }
-static inline void stt_hint_v2(void* p, uint2 v, uint64_t) { memcpy(p, &v, 8); }
-static inline unsigned long long atomic_load_u64(unsigned long long* p) { return *p; }
-static inline unsigned long long atomic_cas_u64(unsigned long long* p, unsigned long long cmp, unsigned long long val) { unsigned long long o = *p; if (o == cmp) *p = val; return o; }
 // cp.async: the copy is DEFERRED until the wait that covers its group (per lane), so that code which reads a unit before
 // waiting for it, or overwrites a ring slot that is still to be read, fails in the emulator as well
 void cp_async16_emu(void* sdst, const void* gsrc);

@@ -94,7 +94,7 @@ def test_encode_unaligned_buffers(skew):
         assert (r, o) == oracle.encode(b)
 
 
-@pytest.mark.parametrize("variant", [1, 20])
+@pytest.mark.parametrize("variant", [1])
 def test_encode_other_duplicate_detectors(variant):
     """The always-exact (vote-per-hash-bit, 32 iterations per round) form of the round gives the same bytes as the default."""
     blocks = [cases.content(m, n, seed=90 + i).tobytes() for i, m in enumerate(cases.MODELS) for n in (65536, 4097)]
@@ -123,39 +123,9 @@ def test_encode_fuzz_small_blocks():
             blocks.append(d); caps.append(cap)
         tune = (int(rng.choice([0, 12, 64])), int(rng.choice([0, 8, 1000])), int(rng.choice([0, 24, 1000])))
         res, outs = emu.encode(blocks, caps, sched_seed=int(rng.integers(1, 1 << 20)), src_skew=int(rng.integers(0, 8)),
-                               dst_skew=int(rng.integers(0, 16)), variant=int(rng.choice([1, 2, 20])), tune=tune)
+                               dst_skew=int(rng.integers(0, 16)), variant=int(rng.choice([1, 2])), tune=tune)
         for b, c, r, o in zip(blocks, caps, res, outs):
             assert (r, o) == oracle.encode(b, cap=c), (trial, len(b), c, tune)
-
-
-def test_encode_lane_per_block_fuzz():
-    """The lane-per-block encoder (one lane per block, 8 find-match iterations per step, table in global memory): random
-    content models, lengths on both sides of the 64 K limit, capacities (every output-limit check), alignments and lane
-    schedules; blocks of very different cost share a warp."""
-    rng = np.random.default_rng(4242)
-    for trial in range(16):
-        blocks, caps = [], []
-        for _ in range(int(rng.integers(20, 60))):
-            n = int(rng.choice([int(rng.integers(0, 64)), int(rng.integers(64, 3000)), int(rng.integers(3000, 12000)), 65536 if rng.integers(8) == 0 else 500,
-                                 int(rng.integers(65530, 66500)) if rng.integers(8) == 0 else 200]))
-            d = cases.content(str(rng.choice(cases.MODELS)), n, seed=int(rng.integers(1 << 30))).tobytes()
-            r, _ = oracle.encode(d)
-            cap = int(rng.choice([n + n // 255 + 16, r, max(r - 1, 0), n, int(rng.integers(0, max(r, 1) + 8))]))
-            blocks.append(d); caps.append(cap)
-        res, outs = emu.encode(blocks, caps, sched_seed=int(rng.integers(1, 1 << 20)), src_skew=int(rng.integers(0, 8)),
-                               dst_skew=int(rng.integers(0, 16)), variant=20)
-        for b, c, r, o in zip(blocks, caps, res, outs):
-            assert (r, o) == oracle.encode(b, cap=c), (trial, len(b), c)
-
-
-def test_encode_lane_per_block_output_limit_sweep():
-    for model, n in (("ETEXT", 1500), ("lowent", 1200), ("E50", 2500), ("E0", 700)):
-        d = cases.content(model, n, seed=5).tobytes()
-        r, _ = oracle.encode(d)
-        caps = list(range(0, r + 3))
-        res, outs = emu.encode([d] * len(caps), caps, sched_seed=8, variant=20)
-        for c, rr, o in zip(caps, res, outs):
-            assert (rr, o) == oracle.encode(d, cap=c), (model, c)
 
 
 def test_encode_schedule_independent():

@@ -12,7 +12,6 @@ ctx = lz4net_b200.Context(0)
 if len(sys.argv) > 3: ctx.set_option("encode_variant", int(sys.argv[3]))
 if len(sys.argv) > 4: ctx.set_option("encode_prefetch", int(sys.argv[4]))
 if len(sys.argv) > 5: ctx.set_option("encode_ctas_per_sm", int(sys.argv[5]))
-if len(sys.argv) > 6: ctx.set_option("encode_lane_warp", int(sys.argv[6]))
 w = Workload(ctx, nb, cls, nb, seed=2)
 for _ in range(3):
     w.encode()

@@ -23,7 +23,6 @@ for cls in CLASSES:
     for ctas, pf, var, lw in [(c, p, v, l) for l in LW for v in VAR for c in CTAS for p in PF]:
         if True:
             ctx.set_option("encode_ctas_per_sm", ctas); ctx.set_option("encode_prefetch", pf); ctx.set_option("encode_variant", var)
-            ctx.set_option("encode_lane_warp", lw)
             w.slots.zero_()
             cs = w.verify()                                            # encode + decode, bit-exact round trip
             lens = w.clen.clone()
