@@ -12,8 +12,10 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace lz4b200;
@@ -62,11 +64,41 @@ struct PinBuf {
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
+// Pageable host memory (a managed caller's `fixed` byte[]): cudaMemcpyAsync from / to it is staged by the driver through
+// its own small pinned buffers, synchronously (measured: 4.5 GB/s round trip against 21 from pinned memory).  The library
+// stages such buffers itself, a pipeline chunk at a time, with a handful of host threads doing the memcpy into / out of
+// its pinned chunk buffers while the previous chunks are on the wire.
+constexpr int STAGE_THREADS = 8;
+constexpr size_t STAGE_PARALLEL_MIN = 4u << 20;
+
+void par_ranges(size_t n, size_t min_parallel, const std::function<void(size_t, size_t)>& fn)
+{
+    if (n < min_parallel) { fn(0, n); return; }
+    std::vector<std::thread> th;
+    const size_t per = (n + STAGE_THREADS - 1) / STAGE_THREADS;
+    for (int t = 1; t < STAGE_THREADS; t++) {
+        const size_t lo = per * t, hi = std::min(n, lo + per);
+        if (lo < hi) th.emplace_back(fn, lo, hi);
+    }
+    fn(0, std::min(n, per));
+    for (auto& t : th) t.join();
+}
+void par_memcpy(void* dst, const void* src, size_t n)
+{
+    par_ranges(n, STAGE_PARALLEL_MIN, [&](size_t lo, size_t hi) { std::memcpy((uint8_t*)dst + lo, (const uint8_t*)src + lo, hi - lo); });
+}
+bool is_pageable(const void* p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
 struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
     DevBuf src, dst, meta, packed, offs, scan;
-    PinBuf hmeta, bounce;
+    PinBuf hmeta, bounce, hsrc, hdst;
 };
 
 }  // namespace
@@ -143,6 +175,7 @@ int run_host(lz4b200_ctx* c, const uint8_t* src, const int64_t* src_off, const i
              uint8_t* dst, const int64_t* dst_off, const int32_t* dst_cap, int32_t* out_len, int32_t n, int op)
 {
     const bool decode = op >= 2;
+    const bool src_pageable = is_pageable(src), dst_pageable = is_pageable(dst);
     int32_t b0 = 0; int k = 0;
     enum Mode { PER_BLOCK, RUNS, PACKED };
     struct Pending { int32_t b0, b1; int64_t dlo; Mode mode; int32_t* h_out; int64_t* h_off; };
@@ -174,9 +207,22 @@ int run_host(lz4b200_ctx* c, const uint8_t* src, const int64_t* src_off, const i
                 CU(sl.bounce.reserve((size_t)total));
                 CU(cudaMemcpyAsync(sl.bounce.p, sl.packed.p, (size_t)total, cudaMemcpyDeviceToHost, sl.stream));
                 CU(cudaStreamSynchronize(sl.stream));
-                for (int32_t i = 0; i < m; i++) {
-                    const int64_t nb = p.h_off[i + 1] - p.h_off[i];
-                    if (nb > 0) std::memcpy(dst + dst_off[p.b0 + i], (const uint8_t*)sl.bounce.p + p.h_off[i], (size_t)nb);
+                const int64_t* h_off = p.h_off; const int32_t pb0 = p.b0; const uint8_t* bounce = (const uint8_t*)sl.bounce.p;
+                par_ranges((size_t)m, total >= (int64_t)STAGE_PARALLEL_MIN ? 1 : (size_t)m + 1, [&](size_t lo, size_t hi) {
+                    for (size_t i = lo; i < hi; i++) {
+                        const int64_t nb = h_off[i + 1] - h_off[i];
+                        if (nb > 0) std::memcpy(dst + dst_off[pb0 + (int32_t)i], bounce + h_off[i], (size_t)nb);
+                    }
+                });
+            }
+        } else if (p.mode == RUNS && dst_pageable) {
+            // the runs landed in the slot's pinned buffer (same layout as the device buffer): out to the caller's memory
+            int32_t r0 = p.b0;
+            for (int32_t i = p.b0 + 1; i <= p.b1; i++) {
+                if (i == p.b1 || dst_off[i] != dst_off[i - 1] + dst_cap[i - 1]) {
+                    const int64_t lo = dst_off[r0], hi = dst_off[i - 1] + dst_cap[i - 1];
+                    if (hi > lo) par_memcpy(dst + lo, (const uint8_t*)sl.hdst.p + (lo - p.dlo), (size_t)(hi - lo));
+                    r0 = i;
                 }
             }
         }
@@ -216,7 +262,11 @@ int run_host(lz4b200_ctx* c, const uint8_t* src, const int64_t* src_off, const i
         }
         uint8_t* d_meta = (uint8_t*)sl.meta.p;
         CU(cudaMemcpyAsync(d_meta, sl.hmeta.p, (size_t)m * 24, cudaMemcpyHostToDevice, sl.stream));
-        if (sbytes) CU(cudaMemcpyAsync(sl.src.p, src + slo, sbytes, cudaMemcpyHostToDevice, sl.stream));
+        if (sbytes) {
+            const uint8_t* from = src + slo;
+            if (src_pageable && m > 8) { CU(sl.hsrc.reserve(sbytes)); par_memcpy(sl.hsrc.p, from, sbytes); from = (const uint8_t*)sl.hsrc.p; }
+            CU(cudaMemcpyAsync(sl.src.p, from, sbytes, cudaMemcpyHostToDevice, sl.stream));
+        }
         BatchArgs a;
         a.src = (const uint8_t*)sl.src.p; a.dst = (uint8_t*)sl.dst.p;
         a.src_off = (const int64_t*)d_meta; a.dst_off = a.src_off + m;
@@ -238,11 +288,13 @@ int run_host(lz4b200_ctx* c, const uint8_t* src, const int64_t* src_off, const i
         }
         CU(cudaMemcpyAsync(h_out, a.out_len, sizeof(int32_t) * (size_t)m, cudaMemcpyDeviceToHost, sl.stream));
         if (mode == RUNS) {
+            if (dst_pageable) CU(sl.hdst.reserve(dbytes));
             int32_t r0 = b0;
             for (int32_t i = b0 + 1; i <= b1; i++) {
                 if (i == b1 || dst_off[i] != dst_off[i - 1] + dst_cap[i - 1]) {
                     const int64_t lo = dst_off[r0], hi = dst_off[i - 1] + dst_cap[i - 1];
-                    if (hi > lo) CU(cudaMemcpyAsync(dst + lo, (uint8_t*)sl.dst.p + (lo - dlo), (size_t)(hi - lo), cudaMemcpyDeviceToHost, sl.stream));
+                    uint8_t* to = dst_pageable ? (uint8_t*)sl.hdst.p + (lo - dlo) : dst + lo;
+                    if (hi > lo) CU(cudaMemcpyAsync(to, (uint8_t*)sl.dst.p + (lo - dlo), (size_t)(hi - lo), cudaMemcpyDeviceToHost, sl.stream));
                     r0 = i;
                 }
             }
@@ -262,6 +314,7 @@ int run_host_encode_packed(lz4b200_ctx* c, const uint8_t* src, const int64_t* sr
                            const int32_t* dst_cap, uint8_t* dst, int64_t dst_total_cap, int64_t* out_off, int32_t* out_len,
                            int32_t n, int op)
 {
+    const bool src_pageable = is_pageable(src), dst_pageable = is_pageable(dst);
     int32_t b0 = 0; int k = 0; int64_t written = 0;
     struct Pending { int32_t b0, b1; int32_t* h_out; int64_t* h_off; };
     Pending pend[NSLOT]; bool busy[NSLOT] = {false, false, false};
@@ -274,11 +327,14 @@ int run_host_encode_packed(lz4b200_ctx* c, const uint8_t* src, const int64_t* sr
         const int32_t m = p.b1 - p.b0;
         const int64_t total = p.h_off[m];
         if (written + total > dst_total_cap) return fail(LZ4B200_E_ARG, "packed destination too small");
-        if (total > 0) CU(cudaMemcpyAsync(dst + written, sl.packed.p, (size_t)total, cudaMemcpyDeviceToHost, sl.stream));
+        const bool stage = dst_pageable && total > 0;
+        if (stage) CU(sl.hdst.reserve((size_t)total));
+        if (total > 0) CU(cudaMemcpyAsync(stage ? sl.hdst.p : (void*)(dst + written), sl.packed.p, (size_t)total, cudaMemcpyDeviceToHost, sl.stream));
         std::memcpy(out_len + p.b0, p.h_out, sizeof(int32_t) * (size_t)m);
         for (int32_t i = 0; i < m; i++) out_off[p.b0 + i] = written + p.h_off[i];
-        written += total;
         CU(cudaStreamSynchronize(sl.stream));
+        if (stage) par_memcpy(dst + written, sl.hdst.p, (size_t)total);
+        written += total;
         busy[s] = false;
         return LZ4B200_OK;
     };
@@ -314,7 +370,11 @@ int run_host_encode_packed(lz4b200_ctx* c, const uint8_t* src, const int64_t* sr
         }
         uint8_t* d_meta = (uint8_t*)sl.meta.p;
         CU(cudaMemcpyAsync(d_meta, sl.hmeta.p, (size_t)m * 24, cudaMemcpyHostToDevice, sl.stream));
-        if (sbytes) CU(cudaMemcpyAsync(sl.src.p, src + slo, sbytes, cudaMemcpyHostToDevice, sl.stream));
+        if (sbytes) {
+            const uint8_t* from = src + slo;
+            if (src_pageable && m > 8) { CU(sl.hsrc.reserve(sbytes)); par_memcpy(sl.hsrc.p, from, sbytes); from = (const uint8_t*)sl.hsrc.p; }
+            CU(cudaMemcpyAsync(sl.src.p, from, sbytes, cudaMemcpyHostToDevice, sl.stream));
+        }
         BatchArgs a;
         a.src = (const uint8_t*)sl.src.p; a.dst = (uint8_t*)sl.dst.p;
         a.src_off = (const int64_t*)d_meta; a.dst_off = a.src_off + m;
@@ -440,7 +500,7 @@ void lz4b200_destroy(lz4b200_ctx* c)
     cudaDeviceSynchronize();
     for (int i = 0; i < NSLOT; i++) {
         Slot& s = c->slot[i];
-        s.src.release(); s.dst.release(); s.meta.release(); s.hmeta.release(); s.packed.release(); s.offs.release(); s.scan.release(); s.bounce.release();
+        s.src.release(); s.dst.release(); s.meta.release(); s.hmeta.release(); s.packed.release(); s.offs.release(); s.scan.release(); s.bounce.release(); s.hsrc.release(); s.hdst.release();
         if (s.done) cudaEventDestroy(s.done);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
