@@ -69,11 +69,6 @@ struct InWords {
         return r;
     }
     static SIMT_MEM uint32_t word(const Raw& r) { return simt::funnel_r(r.lo, r.hi, r.sh); }
-    // The same two loads taken one byte earlier (p >= 1): the pair of words holding byte p-1 always holds bytes p .. p+3 as
-    // well, so the byte BEFORE the word comes for free -- the first comparison of the encoder's backward catch-up.
-    template <int POLICY> SIMT_MEM Raw raw1(int p) const { return raw<POLICY>(p - 1); }
-    static SIMT_MEM uint32_t word1(const Raw& r) { return simt::funnel_rc(r.lo, r.hi, r.sh + 8u); }     // bytes p .. p+3 (shift 32 = the high word)
-    static SIMT_MEM uint32_t prev1(const Raw& r) { return simt::funnel_r(r.lo, r.hi, r.sh) & 255u; }    // byte p-1
 };
 
 // ---- source policies -------------------------------------------------------------------------------------------

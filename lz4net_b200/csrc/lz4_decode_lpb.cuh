@@ -81,6 +81,8 @@ SIMT_DEV void lpb_decode_warp(LpbShared<GEO>* sh, const LpbBatch& a, uint32_t* c
     uint32_t blk = 0;
     const uint8_t* abase = nullptr;     // compressed stream, rounded down to 16 bytes
     uint8_t* gbase = nullptr;           // output block, rounded down to 128 bytes
+    int32_t g128 = 0;                   // the same as a (signed) count of 128-byte units from the batch's rounded base: one shuffle instead of two
+    uint8_t* const dbase128 = (uint8_t*)((uintptr_t)a.dst & ~(uintptr_t)127);
     uint32_t skew = 0, total = 0;       // src - abase; round_up16(skew + isize)
     uint32_t a0 = 0;                    // dst - gbase: "virtual" output position v = op + a0, so that gbase + v is the address
     int isize = 0, cap = 0;
@@ -147,19 +149,43 @@ SIMT_DEV void lpb_decode_warp(LpbShared<GEO>* sh, const LpbBatch& a, uint32_t* c
         uint32_t v4 = vop & ~3u;
         uint32_t c = dsh ? acc << (32u - dsh) : 0u;                // the carried bytes, moved to the top of a word
         uint32_t rem = n;
-        // four words per round trip when the source allows reading that far ahead (always for the input ring and global
-        // memory; in the output ring the words read must lie below the write cursor)
+        // Four words per round trip when the source allows reading that far ahead (always for the input ring and global
+        // memory; in the output ring the words read must lie below the write cursor).  When neither ring wraps inside the
+        // group, every access is base + constant (LDS / STS with immediate offsets: no address arithmetic per word).
         if (K != 1 || vop - s >= 24u) {
             while (rem > 16) {
                 uint32_t q[4];
+                const uint32_t so = K == 0 ? (sp & IMASK) : (sp & (uint32_t)(GEO::OUT - 4));
+                const uint32_t dof = v4 & (uint32_t)(GEO::OUT - 4);
+                const bool flat = dof <= (uint32_t)(GEO::OUT - 16) && (K == 2 || so <= (uint32_t)((K == 0 ? GEO::IN : GEO::OUT) - 20));
+                if (flat) {
+                    if (K == 2) {
 #pragma unroll
-                for (int i = 0; i < 4; i++) q[i] = load_src(kind, sp + 4u + 4u * i);
+                        for (int i = 0; i < 4; i++) q[i] = simt::ldg_u32(gbase + sp + 4u + 4u * i);
+                    } else {
+                        const simt::smem_ref sr = K == 0 ? ir : ow;
+                        const uint32_t sb = K == 0 ? so : l4 + so;
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const uint32_t x = simt::funnel_r(lo, q[i], ssh);
-                    lo = q[i];
-                    simt::sts_u32(ow, oword(l4, v4 + 4u * i), simt::funnel_l(c, x, dsh));
-                    c = x;
+                        for (int i = 0; i < 4; i++) q[i] = simt::lds_u32(sr, sb + 4u + 4u * i);
+                    }
+                    const uint32_t db = l4 + dof;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const uint32_t x = simt::funnel_r(lo, q[i], ssh);
+                        lo = q[i];
+                        simt::sts_u32(ow, db + 4u * i, simt::funnel_l(c, x, dsh));
+                        c = x;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) q[i] = load_src(kind, sp + 4u + 4u * i);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const uint32_t x = simt::funnel_r(lo, q[i], ssh);
+                        lo = q[i];
+                        simt::sts_u32(ow, oword(l4, v4 + 4u * i), simt::funnel_l(c, x, dsh));
+                        c = x;
+                    }
                 }
                 sp += 16; v4 += 16; rem -= 16;
             }
@@ -209,6 +235,7 @@ SIMT_DEV void lpb_decode_warp(LpbShared<GEO>* sh, const LpbBatch& a, uint32_t* c
                     skew = (uint32_t)((uintptr_t)src & 15); abase = src - skew;
                     total = (skew + (uint32_t)isize + 15u) & ~15u;
                     a0 = (uint32_t)((uintptr_t)dst & 127); gbase = dst - a0;
+                    g128 = (int32_t)(((intptr_t)gbase - (intptr_t)dbase128) >> 7);
                     ip = 0; vop = fpos = slo = a0; acc = 0; phase = 0; coop = 0; need_all = false; done = false;
                     simt::cp_async_commit(); simt::cp_async_wait<0>();     // (units the previous block requested but never read)
                     ifill = 0; refill(0);
@@ -225,7 +252,22 @@ SIMT_DEV void lpb_decode_warp(LpbShared<GEO>* sh, const LpbBatch& a, uint32_t* c
 
         if (active && !need_all) {
             // ---------------- header + literals ----------------
-            if (phase == 0) {
+            // The ordinary sequence -- far from the end of both buffers, its bytes resident, runs a lane copies itself -- needs
+            // none of the end-of-block tests of the reference: one guard replaces them (everything else takes the general
+            // code below, which restates them one by one).
+            bool fast_h = false;
+            if (phase == 0 && (uint32_t)(ip + GEO::LOOK) + skew <= iland && ip + GEO::LOOK + 16 <= isize &&
+                (int)(vop - a0) + GEO::MAXL + 12 <= cap) {
+                const uint32_t t = ib(ip);
+                uint32_t L = t >> 4; int p = ip + 1;
+                if (L == 15) { L += ib(p); p++; }                           // (an extension byte of 255 makes L > MAXL: general code)
+                if (L <= (uint32_t)GEO::MAXL) {
+                    token = t;
+                    if (L) append(LpbKind<0>(), (uint32_t)p, L);
+                    ip = p + (int)L; phase = 1; fast_h = true;
+                }
+            }
+            if (phase == 0 && !fast_h) {
                 const int op = (int)(vop - a0);
                 if (ip < isize) fetch(ip, ip + GEO::LOOK < isize ? ip + GEO::LOOK : isize - 1);
                 if (ip >= isize) { result = -ip - 1; done = true; }
@@ -257,7 +299,19 @@ SIMT_DEV void lpb_decode_warp(LpbShared<GEO>* sh, const LpbBatch& a, uint32_t* c
                 }
             }
             // ---------------- offset + match ----------------
-            if (!done && coop == 0 && phase == 1) {
+            bool fast_m = false;
+            if (!done && coop == 0 && phase == 1 && (uint32_t)(ip + 8) + skew <= iland && ip + 16 <= isize &&
+                (int)(vop - a0) + GEO::MAXM + 5 <= cap) {
+                const uint32_t off = ib(ip) | (ib(ip + 1) << 8);
+                uint32_t M = token & 15u; int q = ip + 2;
+                if (M == 15) { M += ib(q); q++; }
+                const uint32_t n = M + 4u, s = vop - off;
+                if (off - 8u <= (uint32_t)(GEO::WIN - 8) && n <= (uint32_t)GEO::MAXM && off <= vop - a0 && s >= slo) {
+                    append(LpbKind<1>(), s, n);
+                    ip = q; phase = 0; fast_m = true;
+                }
+            }
+            if (!done && coop == 0 && phase == 1 && !fast_m) {
                 const int op1 = (int)(vop - a0);
                 fetch(ip, ip + 8 < isize ? ip + 8 : isize - 1);
                 const uint32_t off = ib(ip) | (ib(ip + 1) << 8);            // :862 / :982 (ip + 2 <= isize was checked with the literals)
@@ -327,30 +381,32 @@ SIMT_DEV void lpb_decode_warp(LpbShared<GEO>* sh, const LpbBatch& a, uint32_t* c
                     const uint32_t qi = qbase >> 3;
                     const uint32_t rot = ((mq >> qi) | (mq << (8u - qi))) & 255u;
                     const int k = mq ? (int)(qbase + (((uint32_t)simt::ffs(rot) - 1u + qi) & 7u)) : lane;
-                    const uint32_t klo = simt::shfl(FULL, fpos, k);
-                    const uint32_t kvop = simt::shfl(FULL, vop, k);
-                    const uint64_t gb = (uint64_t)(uintptr_t)gbase;
-                    uint8_t* const kg = (uint8_t*)(uintptr_t)(((uint64_t)simt::shfl(FULL, (uint32_t)(gb >> 32), k) << 32) | simt::shfl(FULL, (uint32_t)gb, k));
+                    // two shuffles describe the served lane's chunk: its 128-byte unit index from the batch's (rounded) base, and
+                    // (ring offset of fpos) << 10 | unflushed bytes -- everything below is chunk relative
+                    const int32_t kunit = (int32_t)simt::shfl(FULL, (uint32_t)(g128 + (int32_t)(fpos >> 7)), k);
+                    const uint32_t kpk = simt::shfl(FULL, ((fpos & (uint32_t)(GEO::OUT - 1)) << 10) | (vop - fpos), k);
                     if (mq) {
-                        const uint32_t cb = klo & ~127u;
-                        uint32_t khi = cb + 128u; if (khi > kvop) khi = kvop;       // (only a lane that is written out completely ends inside a chunk)
-                        const uint32_t b = cb + 16u * j;
-                        const uint32_t k4 = (uint32_t)k * (uint32_t)(GEO::OUT + 4);
+                        const uint32_t fo = kpk >> 10, pend_k = kpk & 1023u;
+                        const uint32_t klo = fo & 127u;                               // first byte of the chunk still to be written
+                        uint32_t khi = klo + pend_k; if (khi > 128u) khi = 128u;      // (only a lane that is written out completely ends inside a chunk)
+                        uint8_t* const kg = dbase128 + (intptr_t)kunit * 128;
+                        const uint32_t kr = (uint32_t)k * (uint32_t)(GEO::OUT + 4) + (fo & ~127u);   // the chunk in lane k's ring (no wrap inside a chunk)
+                        const uint32_t b = 16u * j;
                         if (b >= klo && b + 16u <= khi) {
                             uint4 v;
-                            v.x = simt::lds_u32(ow, oword(k4, b)); v.y = simt::lds_u32(ow, oword(k4, b + 4));
-                            v.z = simt::lds_u32(ow, oword(k4, b + 8)); v.w = simt::lds_u32(ow, oword(k4, b + 12));
+                            v.x = simt::lds_u32(ow, kr + b); v.y = simt::lds_u32(ow, kr + b + 4);
+                            v.z = simt::lds_u32(ow, kr + b + 8); v.w = simt::lds_u32(ow, kr + b + 12);
                             simt::stg_v4(kg + b, v);
                         } else if (b + 16u > klo && b < khi) {                      // the edges of the range: words, then bytes
                             for (uint32_t t = 0; t < 16; t += 4) {
                                 const uint32_t ws = b + t;
                                 if (ws + 4 <= klo || ws >= khi) continue;
-                                const uint32_t w = simt::lds_u32(ow, oword(k4, ws));
+                                const uint32_t w = simt::lds_u32(ow, kr + ws);
                                 if (ws >= klo && ws + 4 <= khi) simt::stg_u32(kg + ws, w);
                                 else for (uint32_t e = 0; e < 4; e++) if (ws + e >= klo && ws + e < khi) simt::stg_u8(kg + ws + e, (uint8_t)(w >> (8u * e)));
                             }
                         }
-                        if (lane == k) fpos = khi;
+                        if (lane == k) fpos += khi - klo;
                     }
                 }
                 simt::syncwarp(FULL);                                       // the stores above -> the served lanes' later loads of their own output

@@ -98,7 +98,7 @@ struct EncTable {
 // input word, moved by SHFL, no load; three or more take the exact path (one vote per hash bit) over the first 32
 // iterations.  At the end every bucket gets its final value: the position of the last sharer whose iteration really
 // ran (index <= f), or its old entry if none did.
-struct RoundOut { int f; bool finished; int ip, ref; bool back1; };   // back1: the bytes before ip and ref are equal (or unknown): a catch-up may follow
+struct RoundOut { int f; bool finished; int ip, ref; };
 
 // SIMPLE: every attempt of the round still has step 1 and lies inside the block (known from two warp-uniform tests):
 // positions are consecutive and every iteration is valid.
@@ -123,17 +123,17 @@ SIMT_DEV RoundOut find_round(const EncTable<GENERAL>& T, const InWords& in, int 
         if (special && lane == 0) pos[s] -= 1;                     // (the formula gives ip-1 and ip for attempts 65 and 66)
     }
 #pragma unroll
-    for (int s = 0; s < W; s++) rp[s] = in.raw1<LDP>(valid[s] ? pos[s] : 1);   // (every probe position is >= 1: the byte before it rides along)
+    for (int s = 0; s < W; s++) rp[s] = in.raw<LDP>(valid[s] ? pos[s] : 0);
 #pragma unroll
     for (int s = 0; s < W; s++) vmask[s] = SIMPLE ? FULL : simt::ballot(FULL, valid[s]);
 #pragma unroll
-    for (int s = 0; s < W; s++) { v[s] = InWords::word1(rp[s]); h[s] = (v[s] * 2654435761u) >> HSHIFT; }
+    for (int s = 0; s < W; s++) { v[s] = InWords::word(rp[s]); h[s] = (v[s] * 2654435761u) >> HSHIFT; }
 #pragma unroll
     for (int s = 0; s < W; s++) t[s] = T.get(h[s]);
 #pragma unroll
-    for (int s = 0; s < W; s++) rc[s] = in.raw1<LDP>(t[s] > 0 ? t[s] : 1);   // candidate words for the table entries (and the byte before each): in flight from here
+    for (int s = 0; s < W; s++) rc[s] = in.raw<LDP>(t[s]);          // candidate words for the table entries: in flight from here
 
-    RoundOut o; o.finished = false; o.ip = o.ref = 0; o.back1 = true;
+    RoundOut o; o.finished = false; o.ip = o.ref = 0;
     int partner[W];
     uint32_t anylost = 0u, multi = 0u;
 #pragma unroll
@@ -163,32 +163,26 @@ SIMT_DEV RoundOut find_round(const EncTable<GENERAL>& T, const InWords& in, int 
         }
     }
     if (DUP == 2 && multi == 0u) {
-        uint32_t hitm[W]; int cand[W]; bool back1[W];
+        uint32_t hitm[W]; int cand[W];
 #pragma unroll
         for (int s = 0; s < W; s++) {
             cand[s] = t[s];
-            uint32_t pv = 0, ppb = 0; bool lowerp = false;
-            if (anylost) {                                          // the earlier sharer's position, input word and the byte before it
+            uint32_t pv = 0; bool lowerp = false;
+            if (anylost) {                                          // the earlier sharer's position and input word
                 const int pl = partner[s] >= 0 ? (partner[s] & 31) : lane;
                 int pp; pv = simt::shfl(FULL, v[0], pl);
-                // (the byte before a position: bits 0-7 of slot 0, 8-15 of slot 1, one shuffle for both)
-                const uint32_t pbs = simt::shfl(FULL, InWords::prev1(rp[0]) | (W == 2 ? InWords::prev1(rp[W - 1]) << 8 : 0u), pl);
-                ppb = pbs & 255u;
                 if (SIMPLE) pp = p0 + partner[s] - ((fused && partner[s] == 0) ? 1 : 0);     // a position follows from its index
                 else pp = (int)simt::shfl(FULL, (uint32_t)pos[0], pl);
                 if (W == 2) {
                     const uint32_t pv1 = simt::shfl(FULL, v[W - 1], pl);
                     if (!SIMPLE) { const int pp1 = (int)simt::shfl(FULL, (uint32_t)pos[W - 1], pl); if (partner[s] >= 32) pp = pp1; }
-                    if (partner[s] >= 32) { pv = pv1; ppb = pbs >> 8; }
+                    if (partner[s] >= 32) pv = pv1;
                 }
                 lowerp = partner[s] >= 0 && partner[s] < 32 * s + lane;
                 if (lowerp) cand[s] = pp;
             }
             simt::tie(rc[s].lo, anylost | multi);                   // wait for the candidate words only after the votes above
-            // the word at a table candidate t: loaded from t-1 (word1) unless t == 0 (loaded from 0: word)
-            const uint32_t w = lowerp ? pv : (t[s] > 0 ? InWords::word1(rc[s]) : InWords::word(rc[s]));
-            const uint32_t cb = lowerp ? ppb : InWords::prev1(rc[s]);
-            back1[s] = cand[s] > 0 && cb == InWords::prev1(rp[s]);  // :432 / :657 first step: ref > 0 and the bytes before ip and ref are equal
+            const uint32_t w = lowerp ? pv : InWords::word(rc[s]);
             const bool hit = valid[s] && !(fused && s == 0 && lane == 0) &&           // (lane 0 of a fused round only inserts)
                              (!GENERAL || cand[s] >= pos[s] - 65535) && w == v[s];    // :429 / :654, :531 / :751
             hitm[s] = simt::ballot(FULL, hit);
@@ -214,8 +208,7 @@ SIMT_DEV RoundOut find_round(const EncTable<GENERAL>& T, const InWords& in, int 
             else {
                 const bool hi = W == 2 && f >= 32;
                 o.ip = SIMPLE ? p0 + f : (int)simt::shfl(FULL, (uint32_t)(hi ? pos[W - 1] : pos[0]), f & 31);   // (f == 0 never hits in a fused round)
-                const uint32_t rb = simt::shfl(FULL, (uint32_t)(hi ? cand[W - 1] : cand[0]) | ((hi ? back1[W - 1] : back1[0]) ? 0x80000000u : 0u), f & 31);
-                o.ref = (int)(rb & 0x7FFFFFFFu); o.back1 = (rb >> 31) != 0;
+                o.ref = (int)simt::shfl(FULL, (uint32_t)(hi ? cand[W - 1] : cand[0]), f & 31);
             }
         }
         return o;
@@ -234,7 +227,7 @@ SIMT_DEV RoundOut find_round(const EncTable<GENERAL>& T, const InWords& in, int 
         const int fwd = (int)simt::shfl(FULL, (uint32_t)pos[0], from);
         const uint32_t fv = simt::shfl(FULL, v[0], from);
         const int cand = lower ? fwd : t[0];
-        const uint32_t w0 = lower ? fv : (t[0] > 0 ? InWords::word1(rc[0]) : InWords::word(rc[0]));
+        const uint32_t w0 = lower ? fv : InWords::word(rc[0]);
         const bool hit = valid[0] && !(fused && lane == 0) && (!GENERAL || cand >= pos[0] - 65535) && w0 == v[0];
         const uint32_t stop = simt::ballot(FULL, !valid[0] || hit);
         const int f = stop ? simt::ffs(stop) - 1 : 32;
@@ -355,7 +348,7 @@ SIMT_DEV int encode_block_t(void* table, const uint8_t* src, int n, uint8_t* dst
         bool probe_first = false;                                  // dense matches: try the post-match probe alone first
         int pfpos = 0;
         for (;;) {
-            int ip = 0, ref = 0; bool again = false, have = false, finished = false, back1 = true;
+            int ip = 0, ref = 0; bool again = false, have = false, finished = false;
             if (probe_first) {
                 // The post-match table operations (:519-531 / :739-751) on their own, warp-uniform: in token-dense data
                 // the probe at ip usually hits (a zero-literal sequence) and a whole round would be wasted work.
@@ -393,7 +386,7 @@ SIMT_DEV int encode_block_t(void* table, const uint8_t* src, int n, uint8_t* dst
                     continue;
                 }
                 if (r.finished) { finished = true; break; }
-                ip = r.ip; ref = r.ref; have = true; back1 = r.back1;
+                ip = r.ip; ref = r.ref; have = true;
                 again = fused && r.f == 1;                          // zero-literal sequence (:531 / :751)
             }
             if (finished) break;
@@ -405,8 +398,7 @@ SIMT_DEV int encode_block_t(void* table, const uint8_t* src, int n, uint8_t* dst
                 const int a = mp + 4 * lane;
                 int room = matchlimit - a; room = room < 0 ? 0 : (room > 4 ? 4 : room);
                 const InWords::Raw ra = in.raw<LDP>(room > 0 ? a : 0), rr = in.raw<LDP>(room > 0 ? mr + 4 * lane : 0);
-                if (ip > anchor && back1) {                         // (never after a zero-literal probe hit: ip == anchor; rarely at all:
-                                                                    //  the round already compared the bytes before ip and ref)
+                if (ip > anchor) {                                  // (never after a zero-literal probe hit: ip == anchor)
                     const int k = lane + 1;
                     const bool okb = ip - k >= anchor && ref - k >= 0;
                     const uint8_t ba = simt::ldg_nc_u8(src + (okb ? ip - k : 0)), bb = simt::ldg_nc_u8(src + (okb ? ref - k : 0));

@@ -27,7 +27,6 @@ SIMT_DEV int ffs(uint32_t v) { return __ffs((int)v); }
 SIMT_DEV int clz(uint32_t v) { return __clz((int)v); }
 SIMT_DEV int popc(uint32_t v) { return __popc(v); }
 SIMT_DEV uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) { return __funnelshift_r(lo, hi, sh); }
-SIMT_DEV uint32_t funnel_rc(uint32_t lo, uint32_t hi, uint32_t sh) { return __funnelshift_rc(lo, hi, sh); }   // shift clamped to 32 (-> hi)
 SIMT_DEV uint32_t funnel_l(uint32_t lo, uint32_t hi, uint32_t sh) { return __funnelshift_l(lo, hi, sh); }     // high word of (hi:lo) << sh
 
 // Opaque identity: stops the compiler from re-deriving a value from its parts at every use (e.g. a 64-bit pointer

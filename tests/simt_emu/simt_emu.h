@@ -34,7 +34,6 @@ static inline int ffs(uint32_t v) { return __builtin_ffs((int)v); }
 static inline int clz(uint32_t v) { return v ? __builtin_clz(v) : 32; }
 static inline int popc(uint32_t v) { return __builtin_popcount(v); }
 static inline uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) { uint64_t t = ((uint64_t)hi << 32) | lo; return (uint32_t)(t >> (sh & 31)); }
-static inline uint32_t funnel_rc(uint32_t lo, uint32_t hi, uint32_t sh) { if (sh >= 32) return hi; uint64_t t = ((uint64_t)hi << 32) | lo; return (uint32_t)(t >> sh); }
 static inline uint32_t funnel_l(uint32_t lo, uint32_t hi, uint32_t sh) { uint64_t t = ((uint64_t)hi << 32) | lo; return (uint32_t)((t << (sh & 31)) >> 32); }
 
 template <class T> static inline T* keep(T* p) { return p; }
