@@ -148,7 +148,7 @@ cudaError_t launch_decode(const BatchArgs& a, bool known_len, int lanes, uint32_
     const bool staged = lanes >= 100;            // lanes = 100 + G selects the output-staged variant
     switch (lanes % 100) {
     case 1:  return known_len ? launch_lpb<true, LpbGeom<256, 512>>(a, counter, dev, stream) : launch_lpb<false, LpbGeom<256, 512>>(a, counter, dev, stream);
-    case 2:  return known_len ? launch_lpb<true, LpbGeom<128, 256, 32, 0>>(a, counter, dev, stream) : launch_lpb<false, LpbGeom<128, 256, 32, 0>>(a, counter, dev, stream);
+    case 2:  return known_len ? launch_lpb<true, LpbGeom<128, 256, 32, 0, 2>>(a, counter, dev, stream) : launch_lpb<false, LpbGeom<128, 256, 32, 0, 2>>(a, counter, dev, stream);
     case 4:  return launch_g<4>(a, known_len, staged, counter, dev, stream);
     case 8:  return launch_g<8>(a, known_len, staged, counter, dev, stream);
     case 16: return launch_g<16>(a, known_len, staged, counter, dev, stream);

@@ -37,9 +37,10 @@ namespace lz4b200 {
 // DEPTH: how many iterations ahead the input is requested (1: a unit is waited for one full iteration after its request,
 // needs IN >= 3 LOOK + 16; 0: requests are waited for at the top of the next iteration, IN >= 2 LOOK + 16 -- the smaller
 // rings let more warps share an SM, which is what hides the latency then).
-template <int IN_, int OUT_, int MAXRUN_ = 64, int DEPTH_ = 1>
+template <int IN_, int OUT_, int MAXRUN_ = 64, int DEPTH_ = 1, int SEQS_ = 1>
 struct LpbGeom {
     static constexpr int IN = IN_, OUT = OUT_, DEPTH = DEPTH_;
+    static constexpr int SEQS = SEQS_;                             // sequences a lane takes per iteration of the warp loop
     static constexpr int IN_STRIDE = IN + 16;                      // == 16 (mod 128): the 128-bit fills of the eight lanes of a phase never collide
     static constexpr int MAXL = MAXRUN_, MAXM = MAXRUN_;           // longest literal run / match a lane copies by itself
     static constexpr int LOOK = 1 + 1 + MAXL + 2 + 1 + 4;          // stream bytes such a sequence can touch (+ word over-read)
@@ -47,7 +48,7 @@ struct LpbGeom {
     static constexpr int CHUNK = 128;                              // flush unit (bytes, aligned in the output buffer)
     static constexpr int HIGH = OUT - 256 > CHUNK ? OUT - 256 : CHUNK;   // a lane with this many unflushed bytes forces a flush step
     static_assert((IN & (IN - 1)) == 0 && (OUT & (OUT - 1)) == 0 && OUT >= 256, "ring sizes");
-    static_assert(IN >= (2 + DEPTH) * LOOK + 16 && HIGH + MAXL + MAXM <= OUT, "ring capacity");
+    static_assert(IN >= (2 + DEPTH) * LOOK + 16 && HIGH + MAXL + MAXM + 8 <= OUT, "ring capacity");
 };
 
 template <class GEO> struct alignas(128) LpbShared {
@@ -149,53 +150,46 @@ SIMT_DEV void lpb_decode_warp(LpbShared<GEO>* sh, const LpbBatch& a, uint32_t* c
         uint32_t v4 = vop & ~3u;
         uint32_t c = dsh ? acc << (32u - dsh) : 0u;                // the carried bytes, moved to the top of a word
         uint32_t rem = n;
-        // Four words per round trip when the source allows reading that far ahead (always for the input ring and global
-        // memory; in the output ring the words read must lie below the write cursor).  When neither ring wraps inside the
-        // group, every access is base + constant (LDS / STS with immediate offsets: no address arithmetic per word).
-        if (K != 1 || vop - s >= 24u) {
-            while (rem > 16) {
-                uint32_t q[4];
-                const uint32_t so = K == 0 ? (sp & IMASK) : (sp & (uint32_t)(GEO::OUT - 4));
-                const uint32_t dof = v4 & (uint32_t)(GEO::OUT - 4);
-                const bool flat = dof <= (uint32_t)(GEO::OUT - 16) && (K == 2 || so <= (uint32_t)((K == 0 ? GEO::IN : GEO::OUT) - 20));
-                if (flat) {
-                    if (K == 2) {
+        // Up to four words per round trip when the source allows reading that far ahead (always for the input ring and
+        // global memory; in the output ring the words read must lie below the write cursor).  When neither ring wraps inside
+        // the group, every access is base + constant (LDS / STS with immediate offsets: no address arithmetic per word).
+        uint32_t full = (rem - 1u) >> 2;                           // whole 4-byte groups before the last group (1..4 bytes)
+        const bool ahead = K != 1 || vop - s >= 24u;
+        while (full > 0) {
+            const uint32_t cnt = ahead ? (full < 4u ? full : 4u) : 1u;
+            uint32_t q[4];
+            const uint32_t so = K == 0 ? (sp & IMASK) : (sp & (uint32_t)(GEO::OUT - 4));
+            const uint32_t dof = v4 & (uint32_t)(GEO::OUT - 4);
+            const bool flat = ahead && dof <= (uint32_t)(GEO::OUT - 16) && (K == 2 || so <= (uint32_t)((K == 0 ? GEO::IN : GEO::OUT) - 20));
+            if (flat) {
+                if (K == 2) {
 #pragma unroll
-                        for (int i = 0; i < 4; i++) q[i] = simt::ldg_u32(gbase + sp + 4u + 4u * i);
-                    } else {
-                        const simt::smem_ref sr = K == 0 ? ir : ow;
-                        const uint32_t sb = K == 0 ? so : l4 + so;
-#pragma unroll
-                        for (int i = 0; i < 4; i++) q[i] = simt::lds_u32(sr, sb + 4u + 4u * i);
-                    }
-                    const uint32_t db = l4 + dof;
-#pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        const uint32_t x = simt::funnel_r(lo, q[i], ssh);
-                        lo = q[i];
-                        simt::sts_u32(ow, db + 4u * i, simt::funnel_l(c, x, dsh));
-                        c = x;
-                    }
+                    for (int i = 0; i < 4; i++) q[i] = simt::ldg_u32(gbase + sp + 4u + 4u * i);
                 } else {
+                    const simt::smem_ref sr = K == 0 ? ir : ow;
+                    const uint32_t sb = K == 0 ? so : l4 + so;
 #pragma unroll
-                    for (int i = 0; i < 4; i++) q[i] = load_src(kind, sp + 4u + 4u * i);
+                    for (int i = 0; i < 4; i++) q[i] = simt::lds_u32(sr, sb + 4u + 4u * i);
+                }
+                const uint32_t db = l4 + dof;
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
+                for (int i = 0; i < 4; i++) {
+                    const uint32_t x = simt::funnel_r(lo, q[i], ssh);
+                    if ((uint32_t)i < cnt) { simt::sts_u32(ow, db + 4u * i, simt::funnel_l(c, x, dsh)); lo = q[i]; c = x; }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; i++) if ((uint32_t)i < cnt) q[i] = load_src(kind, sp + 4u + 4u * i);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    if ((uint32_t)i < cnt) {
                         const uint32_t x = simt::funnel_r(lo, q[i], ssh);
-                        lo = q[i];
                         simt::sts_u32(ow, oword(l4, v4 + 4u * i), simt::funnel_l(c, x, dsh));
-                        c = x;
+                        lo = q[i]; c = x;
                     }
                 }
-                sp += 16; v4 += 16; rem -= 16;
             }
-        }
-        while (rem > 4) {                                          // whole groups of 4 source bytes -> one finished word each
-            const uint32_t hi = load_src(kind, sp + 4);
-            const uint32_t x = simt::funnel_r(lo, hi, ssh);
-            lo = hi; sp += 4;
-            simt::sts_u32(ow, oword(l4, v4), simt::funnel_l(c, x, dsh));
-            c = x; v4 += 4; rem -= 4;
+            sp += 4u * cnt; v4 += 4u * cnt; rem -= 4u * cnt; full -= cnt;
         }
         {                                                          // the last group: 1..4 bytes
             const uint32_t hi = load_src(kind, sp + 4);
@@ -211,7 +205,40 @@ SIMT_DEV void lpb_decode_warp(LpbShared<GEO>* sh, const LpbBatch& a, uint32_t* c
         }
         vop += n;
     };
-    // one byte (overlapping matches closer than 8 bytes; sources that straddle the ring's valid range)
+    // The same for a match whose source is at least 4 bytes back and lies, word by word, either in the output ring
+    // (positions >= rmin: still valid when the append ends) or in global memory (written out earlier).  Every lane of the
+    // warp can take this one path whatever its offset: no read-ahead, two fresh source words per group.
+    auto append_mixed = [&](uint32_t s, uint32_t n, int rmin) {
+        const uint32_t ssh = (s & 3u) * 8u;
+        uint32_t sp = s & ~3u;
+        const uint32_t k = vop & 3u, dsh = k * 8u;
+        uint32_t v4 = vop & ~3u;
+        uint32_t c = dsh ? acc << (32u - dsh) : 0u;
+        uint32_t rem = n;
+        auto ld = [&](uint32_t p4) -> uint32_t { return (int)p4 >= rmin ? simt::lds_u32(ow, oword(l4, p4)) : simt::ldg_u32(gbase + p4); };
+        // closer than 8 bytes, the next group reads bytes this group produced: the part of them that spills into the next
+        // word is written through at once (further back, the carried bytes are stored with the next group early enough)
+        const bool wt = dsh != 0u && vop - s < 8u;
+        while (rem > 4) {
+            const uint32_t x = simt::funnel_r(ld(sp), ld(sp + 4), ssh);
+            simt::sts_u32(ow, oword(l4, v4), simt::funnel_l(c, x, dsh));
+            if (wt) simt::sts_u32(ow, oword(l4, v4 + 4), x >> (32u - dsh));
+            c = x; sp += 4; v4 += 4; rem -= 4;
+        }
+        {
+            uint32_t x = simt::funnel_r(ld(sp), ld(sp + 4), ssh);
+            if (rem < 4) x &= (1u << (8u * rem)) - 1u;
+            const uint32_t carried = dsh ? c >> (32u - dsh) : 0u;
+            const uint32_t w = carried | (x << dsh);
+            simt::sts_u32(ow, oword(l4, v4), w);
+            if (k + rem >= 4) {
+                acc = dsh ? x >> (32u - dsh) : 0u;
+                if (k + rem > 4) simt::sts_u32(ow, oword(l4, v4 + 4), acc);
+            } else acc = w;
+        }
+        vop += n;
+    };
+    // one byte (overlapping matches closer than 4 bytes; sources that straddle the ring's valid range)
     auto append_byte = [&](uint32_t b) {
         const uint32_t k = vop & 3u;
         acc |= b << (8u * k);
@@ -250,7 +277,13 @@ SIMT_DEV void lpb_decode_warp(LpbShared<GEO>* sh, const LpbBatch& a, uint32_t* c
         else { simt::cp_async_wait<1>(); iland = f1; f1 = ifill; }  // (all groups but the one just committed are complete: everything below the previous commit's ifill)
         fresh = false;
 
-        if (active && !need_all) {
+        for (int rep = 0; rep < GEO::SEQS; rep++) {
+          // (a further sequence in the same iteration only while the unflushed bytes plus one more sequence -- and the word
+          // that is written through behind it -- still fit the ring)
+          const bool go = active && !need_all && !done && coop == 0 &&
+                          (rep == 0 || (vop - fpos) + (uint32_t)(GEO::MAXL + GEO::MAXM + 8) <= (uint32_t)GEO::OUT);
+          bool mcan = false, ring8 = false; uint32_t m_s = 0, m_n = 0; int m_q = 0, m_rmin = 0;
+          if (go) {
             // ---------------- header + literals ----------------
             // The ordinary sequence -- far from the end of both buffers, its bytes resident, runs a lane copies itself -- needs
             // none of the end-of-block tests of the reference: one guard replaces them (everything else takes the general
@@ -299,18 +332,31 @@ SIMT_DEV void lpb_decode_warp(LpbShared<GEO>* sh, const LpbBatch& a, uint32_t* c
                 }
             }
             // ---------------- offset + match ----------------
-            bool fast_m = false;
+            // ---------------- offset + match: the ordinary case is parsed here and copied below, on ONE path for the warp ------
             if (!done && coop == 0 && phase == 1 && (uint32_t)(ip + 8) + skew <= iland && ip + 16 <= isize &&
                 (int)(vop - a0) + GEO::MAXM + 5 <= cap) {
                 const uint32_t off = ib(ip) | (ib(ip + 1) << 8);
                 uint32_t M = token & 15u; int q = ip + 2;
                 if (M == 15) { M += ib(q); q++; }
-                const uint32_t n = M + 4u, s = vop - off;
-                if (off - 8u <= (uint32_t)(GEO::WIN - 8) && n <= (uint32_t)GEO::MAXM && off <= vop - a0 && s >= slo) {
-                    append(LpbKind<1>(), s, n);
-                    ip = q; phase = 0; fast_m = true;
+                const uint32_t n = M + 4u, sv = vop - off;
+                // ring words: positions >= rmin (valid until the append ends); anything below must be in global memory already
+                int rmin = (int)(vop + n + 4u) - GEO::OUT; if (rmin < (int)slo) rmin = (int)slo;
+                rmin = (rmin + 3) & ~3;
+                if (off >= 4u && n <= (uint32_t)GEO::MAXM && off <= vop - a0 && ((int)(sv & ~3u) >= rmin || (int)fpos >= rmin)) {
+                    mcan = true; m_s = sv; m_n = n; m_q = q; m_rmin = rmin;
+                    ring8 = off >= 8u && (int)(sv & ~3u) >= rmin;
                 }
             }
+          }
+          {
+            const uint32_t anym = simt::ballot(FULL, mcan), mixed = simt::ballot(FULL, mcan && !ring8);
+            if (anym) {
+                if (!mixed) { if (mcan) { append(LpbKind<1>(), m_s, m_n); ip = m_q; phase = 0; } }
+                else if (mcan) { append_mixed(m_s, m_n, m_rmin); ip = m_q; phase = 0; }
+            }
+          }
+          if (go) {
+            const bool fast_m = mcan;
             if (!done && coop == 0 && phase == 1 && !fast_m) {
                 const int op1 = (int)(vop - a0);
                 fetch(ip, ip + 8 < isize ? ip + 8 : isize - 1);
@@ -358,6 +404,7 @@ SIMT_DEV void lpb_decode_warp(LpbShared<GEO>* sh, const LpbBatch& a, uint32_t* c
                 done = true;
             }
             if (done || coop) need_all = true;                              // the end of the block / the warp's copy: everything out first
+          }
         }
         // ---------------- finished chunks -> global memory, four lanes per step --------------------------------------------
         // A step serves, per quarter warp, the lowest lane of that quarter that wants it: its eight lanes read 16 bytes each

@@ -65,7 +65,7 @@ void lpb_entry(int lane, void* arg)
 {
     LpbJob* j = (LpbJob*)arg;
     if (j->geo == 1) {
-        typedef LpbGeom<128, 256, 32, 0> G;
+        typedef LpbGeom<128, 256, 32, 0, 2> G;
         j->known ? lpb_decode_warp<true, G>((LpbShared<G>*)j->sh, j->a, &j->counter, lane) : lpb_decode_warp<false, G>((LpbShared<G>*)j->sh, j->a, &j->counter, lane);
     } else {
         typedef LpbGeom<256, 512> G;

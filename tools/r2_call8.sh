@@ -2,7 +2,7 @@
 set -u
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
-T=r2c8
+T=r2c9
 echo "=== pytest decode ==="
 timeout 900 python -m pytest tests -m gpu -x -q -k "decode or roundtrip or large_batch" 2>&1 | tail -4 | tee gpurun_out/${T}_pytest.txt
 echo "=== decoder sweep ==="
