@@ -96,10 +96,12 @@ static cudaError_t launch_g(const BatchArgs& a, bool known, bool staged, uint32_
 }
 
 // ---- lane-per-block decoder (lz4_decode_lpb.cuh): one CTA per SM, as many warps as shared memory holds rings for --------
-constexpr int LPB_MAX_WARPS = 17;
+// Warps per CTA: what 227 KiB of shared memory hold rings for, rounded DOWN to a multiple of four -- ptxas budgets registers
+// for the block size rounded up to 128 threads (17 warps were given the 96 registers of 20 and spilled the copy loops).
+template <class GEO> constexpr int lpb_warps() { return (int)((232448 / sizeof(LpbShared<GEO>)) / 4 * 4) > 0 ? (int)((232448 / sizeof(LpbShared<GEO>)) / 4 * 4) : 1; }
 
 template <bool KNOWN, class GEO>
-__global__ void __launch_bounds__(32 * LPB_MAX_WARPS, 1)
+__global__ void __launch_bounds__(32 * lpb_warps<GEO>(), 1)
 lz4_decode_lpb_kernel(BatchArgs a, uint32_t* counter)
 {
     extern __shared__ __align__(128) uint8_t lpb_smem[];
@@ -112,7 +114,7 @@ template <bool KNOWN, class GEO>
 static cudaError_t launch_lpb(const BatchArgs& a, uint32_t* counter, const DeviceInfo& dev, cudaStream_t stream)
 {
     int warps = dev.smem_optin / (int)sizeof(LpbShared<GEO>);
-    if (warps > LPB_MAX_WARPS) warps = LPB_MAX_WARPS;
+    if (warps > lpb_warps<GEO>()) warps = lpb_warps<GEO>();
     if (warps < 1) return cudaErrorInvalidConfiguration;
     long long grid = dev.num_sms;
     const long long want_warps = ((long long)a.n_blocks + 31) / 32;          // one block per lane
