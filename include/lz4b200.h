@@ -143,7 +143,7 @@ int lz4b200_synth_fill(lz4b200_ctx* ctx, void* dst, int64_t n_blocks, int32_t bl
                        int64_t first_block, void* stream);
 
 /* Tuning knobs (bench / profiling only).  key: "decode_lanes" (4|8|16|32 lanes per block, +100 = the output-staged
- * variant; 1 | 2 = the lane-per-block decoder with a 512- / 256-byte output window), "decode_lanes_auto" (the decoder is
+ * variant; 1 = the lane-per-block decoder), "decode_lanes_auto" (the decoder is
  * picked per batch from the compression ratio: the default), "encode_ctas_per_sm" (encoder warps = blocks in
  * flight per SM, 0 = as many as shared memory allows: 14), "encode_variant" (1 = always exact same-hash votes, 2 = resolved
  * through the table: default),

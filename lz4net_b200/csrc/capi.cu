@@ -137,7 +137,11 @@ struct DeviceGuard {
 // Decode group size from the ratio compressed/raw of a batch (tools/sweep.py): incompressible data is long literal runs
 // (whole warps, 128-bit copies), nearly-empty streams are long matches, everything between is sequence-dense (the
 // denser, the smaller the group: 8 lanes around ratio 0.58, 4 lanes around 0.37; both output-staged).
-int lanes_for_ratio(double ratio, int64_t n_blocks) { (void)n_blocks; return decode_lanes_for_ratio(ratio); }
+int lanes_for_ratio(double ratio, int64_t n_blocks, const DeviceInfo& dev)
+{
+    const int g = decode_lanes_for_ratio(ratio);
+    return (g == 104 || g == 108) && n_blocks >= (int64_t)dev.num_sms * 32 * 8 ? 1 : g;    // sequence-dense + many blocks: one lane per block
+}
 
 int run_device(lz4b200_ctx* c, const BatchArgs& a, int op /*0 enc fast, 1 enc hc, 2 dec known, 3 dec unknown*/, cudaStream_t st, int lanes = 0)
 {
@@ -276,7 +280,7 @@ int run_host(lz4b200_ctx* c, const uint8_t* src, const int64_t* src_off, const i
         if (decode && c->decode_lanes_auto) {
             double cs = 0, rs = 0;
             for (int32_t i = b0; i < b1; i++) { cs += src_len[i]; rs += dst_cap[i]; }
-            lanes = lanes_for_ratio(rs > 0 ? cs / rs : 1.0, m);
+            lanes = lanes_for_ratio(rs > 0 ? cs / rs : 1.0, m, c->dev);
         }
         rc = run_device(c, a, op, sl.stream, lanes); if (rc) return rc;
         if (mode == PACKED) {
@@ -587,8 +591,8 @@ int lz4b200_set_option(lz4b200_ctx* c, const char* key, int64_t value)
     std::string k(key);
     if (k == "decode_lanes") {
         const int64_t g = value % 100;                 // 100 + G = the output-staged variant of the G-lane decoder
-        const bool lpb = value == 1 || value == 2;     // one lane per block (512- / 256-byte output ring)
-        if (!lpb && ((g != 4 && g != 8 && g != 16 && g != 32) || (value != g && value != 100 + g))) return fail(LZ4B200_E_ARG, "decode_lanes must be 1, 2, 4, 8, 16, 32 (or 100 + one of the last four)");
+        const bool lpb = value == 1;                   // one lane per block (lz4_decode_lpb.cuh)
+        if (!lpb && ((g != 4 && g != 8 && g != 16 && g != 32) || (value != g && value != 100 + g))) return fail(LZ4B200_E_ARG, "decode_lanes must be 1, 4, 8, 16, 32 (or 100 + one of the last four)");
         c->decode_lanes = (int)value; c->decode_lanes_auto = false;
     }
     else if (k == "decode_lanes_auto") { c->decode_lanes_auto = value != 0; }

@@ -96,22 +96,31 @@ static cudaError_t launch_g(const BatchArgs& a, bool known, bool staged, uint32_
 }
 
 // ---- lane-per-block decoder (lz4_decode_lpb.cuh): one CTA per SM, as many warps as shared memory holds rings for --------
+// Geometry (tools/sweep.py, round 2): 128-byte input ring, 256-byte output window, runs up to 32 bytes copied by the lane,
+// requests waited for at the top of the next iteration, two sequences per iteration: 16 warps = 512 blocks in flight per SM.
+// (256 / 512-byte rings with 64-byte runs and one-iteration-ahead requests -- 8 warps -- measured 1078 vs 1406 GB/s on E50
+// and 173 vs 269 GB/s on ETEXT: this kernel lives on resident warps.)
+typedef LpbGeom<128, 256, 32, 0, 2> LpbDefault;
 // Warps per CTA: what 227 KiB of shared memory hold rings for, rounded DOWN to a multiple of four -- ptxas budgets registers
 // for the block size rounded up to 128 threads (17 warps were given the 96 registers of 20 and spilled the copy loops).
 template <class GEO> constexpr int lpb_warps() { return (int)((232448 / sizeof(LpbShared<GEO>)) / 4 * 4) > 0 ? (int)((232448 / sizeof(LpbShared<GEO>)) / 4 * 4) : 1; }
 
 template <bool KNOWN, class GEO>
 __global__ void __launch_bounds__(32 * lpb_warps<GEO>(), 1)
-lz4_decode_lpb_kernel(BatchArgs a, uint32_t* counter)
+lz4_decode_lpb_kernel(BatchArgs a, uint32_t* counter, const int* pick)
 {
+    if (pick && *pick != 104 && *pick != 108) return;                       // auto-selected launches: the sequence-dense classes are this kernel's
     extern __shared__ __align__(128) uint8_t lpb_smem[];
     LpbShared<GEO>* sh = (LpbShared<GEO>*)lpb_smem + (threadIdx.x >> 5);
     const LpbBatch b{a.src, a.src_off, a.src_len, a.dst, a.dst_off, a.dst_cap, a.out_len, a.n_blocks};
     lpb_decode_warp<KNOWN, GEO>(sh, b, counter, (int)(threadIdx.x & 31));
 }
 
+// the lane-per-block decoder wants a block for most of its lanes: below half a wave the group kernels are ahead
+static bool lpb_pays(int64_t n_blocks, const DeviceInfo& dev) { return n_blocks >= (int64_t)dev.num_sms * 32 * 8; }
+
 template <bool KNOWN, class GEO>
-static cudaError_t launch_lpb(const BatchArgs& a, uint32_t* counter, const DeviceInfo& dev, cudaStream_t stream)
+static cudaError_t launch_lpb(const BatchArgs& a, uint32_t* counter, const DeviceInfo& dev, cudaStream_t stream, const int* pick = nullptr)
 {
     int warps = dev.smem_optin / (int)sizeof(LpbShared<GEO>);
     if (warps > lpb_warps<GEO>()) warps = lpb_warps<GEO>();
@@ -125,7 +134,7 @@ static cudaError_t launch_lpb(const BatchArgs& a, uint32_t* counter, const Devic
     const int dyn = warps * (int)sizeof(LpbShared<GEO>);
     cudaError_t e = cudaFuncSetAttribute(lz4_decode_lpb_kernel<KNOWN, GEO>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
     if (e != cudaSuccess) return e;
-    lz4_decode_lpb_kernel<KNOWN, GEO><<<(unsigned)grid, 32 * warps, dyn, stream>>>(a, counter);
+    lz4_decode_lpb_kernel<KNOWN, GEO><<<(unsigned)grid, 32 * warps, dyn, stream>>>(a, counter, pick);
     return cudaGetLastError();
 }
 
@@ -141,16 +150,20 @@ cudaError_t launch_decode(const BatchArgs& a, bool known_len, int lanes, uint32_
         int* pick = (int*)(counter + 1);             // (the context hands out counters in pairs: [block counter, pick])
         lz4_decode_pick_kernel<<<1, 256, 0, stream>>>(a.src_len, a.dst_cap, a.n_blocks, pick);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        if (launches) *launches += 4;
         if ((e = launch_g<32>(a, known_len, false, counter, dev, stream, pick, 32)) != cudaSuccess) return e;
         if ((e = launch_g<16>(a, known_len, false, counter, dev, stream, pick, 16)) != cudaSuccess) return e;
+        if (lpb_pays(a.n_blocks, dev)) {
+            // sequence-dense data, enough blocks to give most lanes one: the lane-per-block decoder
+            if (launches) *launches += 3;
+            return known_len ? launch_lpb<true, LpbDefault>(a, counter, dev, stream, pick) : launch_lpb<false, LpbDefault>(a, counter, dev, stream, pick);
+        }
+        if (launches) *launches += 4;
         if ((e = launch_g<8>(a, known_len, true, counter, dev, stream, pick, 108)) != cudaSuccess) return e;
         return launch_g<4>(a, known_len, true, counter, dev, stream, pick, 104);
     }
     const bool staged = lanes >= 100;            // lanes = 100 + G selects the output-staged variant
     switch (lanes % 100) {
-    case 1:  return known_len ? launch_lpb<true, LpbGeom<256, 512>>(a, counter, dev, stream) : launch_lpb<false, LpbGeom<256, 512>>(a, counter, dev, stream);
-    case 2:  return known_len ? launch_lpb<true, LpbGeom<128, 256, 32, 0, 2>>(a, counter, dev, stream) : launch_lpb<false, LpbGeom<128, 256, 32, 0, 2>>(a, counter, dev, stream);
+    case 1:  return known_len ? launch_lpb<true, LpbDefault>(a, counter, dev, stream) : launch_lpb<false, LpbDefault>(a, counter, dev, stream);
     case 4:  return launch_g<4>(a, known_len, staged, counter, dev, stream);
     case 8:  return launch_g<8>(a, known_len, staged, counter, dev, stream);
     case 16: return launch_g<16>(a, known_len, staged, counter, dev, stream);

@@ -55,7 +55,7 @@ def decode(blocks, caps, lanes=32, known=True, sched_seed=1, src_skew=0, dst_ske
     res = np.zeros(n, np.int32)
     sp = (C.c_void_p * n)(*[a.ctypes.data + src_skew for a in srcs])
     dp = (C.c_void_p * n)(*[a.ctypes.data + 32 + dst_skew for a in dsts])       # 32-byte red zone in front
-    if lanes in (1, 2):      # lane-per-block decoder (1: 512-byte output ring, 2: 256-byte)
+    if lanes in (1, 2):      # lane-per-block decoder (1: the kernel's geometry, 2: larger rings / 64-byte runs / one sequence per iteration)
         lib().emu_decode_lpb(lanes - 1, int(known), n, sp, isz.ctypes.data_as(C.c_void_p), dp, cps.ctypes.data_as(C.c_void_p),
                              res.ctypes.data_as(C.c_void_p), C.c_uint64(sched_seed))
     else:

@@ -64,11 +64,13 @@ struct LpbJob { LpbBatch a; uint32_t counter; int known; int geo; void* sh; };
 void lpb_entry(int lane, void* arg)
 {
     LpbJob* j = (LpbJob*)arg;
+    // geo 0: the kernel's geometry; geo 1: larger rings, 64-byte runs, requests one iteration ahead, one sequence per iteration
+    // (every template path of the header stays compiled and tested)
     if (j->geo == 1) {
-        typedef LpbGeom<128, 256, 32, 0, 2> G;
+        typedef LpbGeom<256, 512, 64, 1, 1> G;
         j->known ? lpb_decode_warp<true, G>((LpbShared<G>*)j->sh, j->a, &j->counter, lane) : lpb_decode_warp<false, G>((LpbShared<G>*)j->sh, j->a, &j->counter, lane);
     } else {
-        typedef LpbGeom<256, 512> G;
+        typedef LpbGeom<128, 256, 32, 0, 2> G;
         j->known ? lpb_decode_warp<true, G>((LpbShared<G>*)j->sh, j->a, &j->counter, lane) : lpb_decode_warp<false, G>((LpbShared<G>*)j->sh, j->a, &j->counter, lane);
     }
 }

@@ -14,6 +14,6 @@ echo "=== ncu launch list ==="
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py $SMALL > gpurun_out/ncu_launch_$TAG.log 2>&1
 grep -c lz4 gpurun_out/launches_$TAG.csv
 echo "=== ncu full: decode ==="
-ncu --set full --clock-control none --import-source on -k regex:lz4_decode -s 3 -c 1 -f -o gpurun_out/dec_$TAG python bench.py $SMALL > gpurun_out/ncu_dec_$TAG.log 2>&1; tail -1 gpurun_out/ncu_dec_$TAG.log
+ncu --set full --clock-control none --import-source on -k regex:lz4_decode_lpb -s 3 -c 1 -f -o gpurun_out/dec_$TAG python bench.py $SMALL > gpurun_out/ncu_dec_$TAG.log 2>&1; tail -1 gpurun_out/ncu_dec_$TAG.log
 echo "=== ncu full: encode ==="
 ncu --set full --clock-control none --import-source on -k regex:lz4_encode_fast -s 3 -c 1 -f -o gpurun_out/enc_$TAG python bench.py $SMALL > gpurun_out/ncu_enc_$TAG.log 2>&1; tail -1 gpurun_out/ncu_enc_$TAG.log
