@@ -140,7 +140,9 @@ struct DeviceGuard {
 int lanes_for_ratio(double ratio, int64_t n_blocks, const DeviceInfo& dev)
 {
     const int g = decode_lanes_for_ratio(ratio);
-    return (g == 104 || g == 108) && n_blocks >= (int64_t)dev.num_sms * 32 * 8 ? 1 : g;    // sequence-dense + many blocks: one lane per block
+    // token-dense + at least half a wave of blocks: one lane per block (decode.cu lpb_pays; host chunks rarely fill whole
+    // waves, so the middle class stays with the 8-lane group kernel)
+    return g == 104 && n_blocks >= (int64_t)dev.num_sms * 32 * 8 ? 1 : g;
 }
 
 int run_device(lz4b200_ctx* c, const BatchArgs& a, int op /*0 enc fast, 1 enc hc, 2 dec known, 3 dec unknown*/, cudaStream_t st, int lanes = 0)

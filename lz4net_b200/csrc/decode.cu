@@ -103,24 +103,36 @@ static cudaError_t launch_g(const BatchArgs& a, bool known, bool staged, uint32_
 typedef LpbGeom<128, 256, 32, 0, 2> LpbDefault;
 // Warps per CTA: what 227 KiB of shared memory hold rings for, rounded DOWN to a multiple of four -- ptxas budgets registers
 // for the block size rounded up to 128 threads (17 warps were given the 96 registers of 20 and spilled the copy loops).
+template <int IN_, int OUT_, int MAXRUN_, int DEPTH_, int SEQS_> struct LpbGeom;
 template <class GEO> constexpr int lpb_warps() { return (int)((232448 / sizeof(LpbShared<GEO>)) / 4 * 4) > 0 ? (int)((232448 / sizeof(LpbShared<GEO>)) / 4 * 4) : 1; }
 
 template <bool KNOWN, class GEO>
 __global__ void __launch_bounds__(32 * lpb_warps<GEO>(), 1)
-lz4_decode_lpb_kernel(BatchArgs a, uint32_t* counter, const int* pick)
+lz4_decode_lpb_kernel(BatchArgs a, uint32_t* counter, const int* pick, int takes108)
 {
-    if (pick && *pick != 104 && *pick != 108) return;                       // auto-selected launches: the sequence-dense classes are this kernel's
+    // auto-selected launches: the dense class (104) is this kernel's, the middle class (108) when the batch fills its waves
+    if (pick && *pick != 104 && !(takes108 && *pick == 108)) return;
     extern __shared__ __align__(128) uint8_t lpb_smem[];
     LpbShared<GEO>* sh = (LpbShared<GEO>*)lpb_smem + (threadIdx.x >> 5);
     const LpbBatch b{a.src, a.src_off, a.src_len, a.dst, a.dst_off, a.dst_cap, a.out_len, a.n_blocks};
     lpb_decode_warp<KNOWN, GEO>(sh, b, counter, (int)(threadIdx.x & 31));
 }
 
-// the lane-per-block decoder wants a block for most of its lanes: below half a wave the group kernels are ahead
-static bool lpb_pays(int64_t n_blocks, const DeviceInfo& dev) { return n_blocks >= (int64_t)dev.num_sms * 32 * 8; }
+// The lane-per-block decoder holds one block per lane (148 x 16 x 32 = 75 776 at a time) and blocks of one class take
+// about equally long, so a batch is worked off in waves: below half a wave the group kernels are ahead; on token-dense
+// data (class 104) it is 1.4-1.6x the 4-lane group kernel and pays from there on; on the middle class (108) its edge over
+// the 8-lane kernel is ~11 %, which a last wave that is less than ~90 % full gives back.
+static bool lpb_pays(int64_t n_blocks, const DeviceInfo& dev, bool middle_class)
+{
+    const int64_t wave = (int64_t)dev.num_sms * 32 * lpb_warps<LpbDefault>();
+    if (n_blocks * 2 < wave) return false;
+    if (!middle_class) return true;
+    const int64_t waves = (n_blocks + wave - 1) / wave;
+    return n_blocks * 10 >= waves * wave * 9;
+}
 
 template <bool KNOWN, class GEO>
-static cudaError_t launch_lpb(const BatchArgs& a, uint32_t* counter, const DeviceInfo& dev, cudaStream_t stream, const int* pick = nullptr)
+static cudaError_t launch_lpb(const BatchArgs& a, uint32_t* counter, const DeviceInfo& dev, cudaStream_t stream, const int* pick = nullptr, int takes108 = 1)
 {
     int warps = dev.smem_optin / (int)sizeof(LpbShared<GEO>);
     if (warps > lpb_warps<GEO>()) warps = lpb_warps<GEO>();
@@ -134,7 +146,7 @@ static cudaError_t launch_lpb(const BatchArgs& a, uint32_t* counter, const Devic
     const int dyn = warps * (int)sizeof(LpbShared<GEO>);
     cudaError_t e = cudaFuncSetAttribute(lz4_decode_lpb_kernel<KNOWN, GEO>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
     if (e != cudaSuccess) return e;
-    lz4_decode_lpb_kernel<KNOWN, GEO><<<(unsigned)grid, 32 * warps, dyn, stream>>>(a, counter, pick);
+    lz4_decode_lpb_kernel<KNOWN, GEO><<<(unsigned)grid, 32 * warps, dyn, stream>>>(a, counter, pick, takes108);
     return cudaGetLastError();
 }
 
@@ -152,14 +164,15 @@ cudaError_t launch_decode(const BatchArgs& a, bool known_len, int lanes, uint32_
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         if ((e = launch_g<32>(a, known_len, false, counter, dev, stream, pick, 32)) != cudaSuccess) return e;
         if ((e = launch_g<16>(a, known_len, false, counter, dev, stream, pick, 16)) != cudaSuccess) return e;
-        if (lpb_pays(a.n_blocks, dev)) {
-            // sequence-dense data, enough blocks to give most lanes one: the lane-per-block decoder
-            if (launches) *launches += 3;
-            return known_len ? launch_lpb<true, LpbDefault>(a, counter, dev, stream, pick) : launch_lpb<false, LpbDefault>(a, counter, dev, stream, pick);
+        const bool lpb104 = lpb_pays(a.n_blocks, dev, false), lpb108 = lpb_pays(a.n_blocks, dev, true);
+        if (launches) *launches += 2 + (lpb104 ? 1 : 0) + (lpb108 ? 0 : 1) + (lpb104 ? 0 : 1);
+        if (lpb104) {
+            e = known_len ? launch_lpb<true, LpbDefault>(a, counter, dev, stream, pick, lpb108 ? 1 : 0) : launch_lpb<false, LpbDefault>(a, counter, dev, stream, pick, lpb108 ? 1 : 0);
+            if (e != cudaSuccess) return e;
         }
-        if (launches) *launches += 4;
-        if ((e = launch_g<8>(a, known_len, true, counter, dev, stream, pick, 108)) != cudaSuccess) return e;
-        return launch_g<4>(a, known_len, true, counter, dev, stream, pick, 104);
+        if (!lpb108 && (e = launch_g<8>(a, known_len, true, counter, dev, stream, pick, 108)) != cudaSuccess) return e;
+        if (!lpb104 && (e = launch_g<4>(a, known_len, true, counter, dev, stream, pick, 104)) != cudaSuccess) return e;
+        return cudaSuccess;
     }
     const bool staged = lanes >= 100;            // lanes = 100 + G selects the output-staged variant
     switch (lanes % 100) {
