@@ -421,6 +421,27 @@ def stream_section(ctx, args, rank, world, dev):
         e2.record(); torch.cuda.synchronize()
         te, td = shard.reduce_max([e0.elapsed_time(e1) * 1e-3, e1.elapsed_time(e2) * 1e-3], device="cuda")
         best = (te, td)
+    # ---- the same stream with the limiter removed: the blocks LAND sharded (rank r holds its contiguous block range, as a
+    # multi-GPU producer would leave them) and stay sharded; the only exchange is 4 bytes of length per block (all-gather).
+    a, b = shard.strong_range(rank, world, nb)
+    mine = torch.empty(max(b - a, 1) * BLOCK, dtype=torch.uint8, device=dev)
+    for b0 in range(a, b, 65536):
+        batch.synth_fill(ctx, mine[(b0 - a) * BLOCK:], min(65536, b - b0), BLOCK, synth.CLASS_ID[args.cls], seed=6, first_block=b0)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1, e2 = ev(), ev(), ev()
+    e0.record()
+    rp, rl = enc(mine[: (b - a) * BLOCK], b - a)
+    if world > 1 and nb % world == 0:
+        lens_all = [torch.empty(shard.strong_range(r, world, nb)[1] - shard.strong_range(r, world, nb)[0], dtype=torch.int32, device=dev) for r in range(world)]
+        dist.all_gather(lens_all, rl)                           # (block counts differ by at most one: equal here, 2^18 blocks)
+    e1.record()
+    rback = dec(rp, rl, b - a)
+    e2.record(); torch.cuda.synchronize()
+    rte, rtd = shard.reduce_max([e0.elapsed_time(e1) * 1e-3, e1.elapsed_time(e2) * 1e-3], device="cuda")
+    rok, = shard.reduce_sum([0.0 if torch.equal(rback, mine[: (b - a) * BLOCK]) else 1.0], device="cuda")
+    del mine, rback, rp
     res = None
     if rank == 0:
         ok = bool(torch.equal(back, raw))
@@ -445,7 +466,10 @@ def stream_section(ctx, args, rank, world, dev):
                "root_link": {"encode_out_bytes": int(n * far), "encode_in_bytes": int(comp * far), "decode_out_bytes": int(comp * far), "decode_in_bytes": int(n * far),
                              "decode_in_gbs_if_only_transfer": None if world == 1 else round(n * far / td / GB, 1)},
                "limiter": "none (one GPU: no transfer)" if world == 1 else
-                          "the root's NVLink ports: every raw byte leaves rank 0 before it is encoded and comes back to it after it is decoded (kernel time is 1/N of the one-GPU time)"}
+                          "the root's NVLink ports: every raw byte leaves rank 0 before it is encoded and comes back to it after it is decoded (kernel time is 1/N of the one-GPU time)",
+               # the limiter removed: the same stream landed sharded, outputs left sharded, 4 bytes per block exchanged
+               "resident": {"encode_gbs": round(n / rte / GB, 1), "decode_gbs": round(n / rtd / GB, 1), "roundtrip_gbs": round(n / (rte + rtd) / GB, 1),
+                            "roundtrip_exact": rok == 0.0, "exchange": "all-gather of int32 lengths only"}}
     del raw
     torch.cuda.empty_cache()
     return res

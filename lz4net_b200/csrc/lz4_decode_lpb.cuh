@@ -205,48 +205,38 @@ SIMT_DEV void lpb_decode_warp(LpbShared<GEO>* sh, const LpbBatch& a, uint32_t* c
         }
         vop += n;
     };
-    // The match path of the WHOLE warp when not every lane's source is in its ring and 8 back: called by all 32 lanes
-    // (`on`: this lane has a match to copy; n <= MAXM bytes from virtual position s, at least 4 back), G = the largest
-    // group count among them (uniform).  Per 4-byte group the source is two aligned words, each from the output ring
-    // (positions >= rmin: valid until the append ends) or from global memory (written out earlier), by predicate -- one
-    // instruction stream whatever the lanes' offsets.  Lanes whose whole source is in global memory and cannot overlap the
-    // destination request all their words before the first is used (one memory round trip per match, not one per group).
-    auto append_mixed = [&](bool on, uint32_t s, uint32_t n, int rmin, uint32_t G) {
-        constexpr int MAXG = (GEO::MAXM + 3) / 4;
+    // The same for a match whose source is at least 4 bytes back and lies, word by word, either in the output ring
+    // (positions >= rmin: still valid when the append ends) or in global memory (written out earlier).  Every lane of the
+    // warp can take this one path whatever its offset: no read-ahead, two fresh source words per group.
+    auto append_mixed = [&](uint32_t s, uint32_t n, int rmin) {
         const uint32_t ssh = (s & 3u) * 8u;
-        const uint32_t sp = s & ~3u;
+        uint32_t sp = s & ~3u;
         const uint32_t k = vop & 3u, dsh = k * 8u;
-        const uint32_t v4 = vop & ~3u;
+        uint32_t v4 = vop & ~3u;
         uint32_t c = dsh ? acc << (32u - dsh) : 0u;
-        const uint32_t myg = on ? (n + 3u) >> 2 : 0u;              // this lane's group count
-        const bool far = on && (int)(sp + 4u * myg + 4u) <= rmin && vop - s >= (uint32_t)(GEO::MAXM + 8);
-        uint32_t q[MAXG + 1];
-#pragma unroll
-        for (int i = 0; i <= MAXG; i++) q[i] = (far && (uint32_t)i <= myg) ? simt::ldg_u32(gbase + sp + 4u * i) : 0u;
+        uint32_t rem = n;
         auto ld = [&](uint32_t p4) -> uint32_t { return (int)p4 >= rmin ? simt::lds_u32(ow, oword(l4, p4)) : simt::ldg_u32(gbase + p4); };
-        // closer than 8 bytes, the next group reads bytes this group produced: what spills into the next word is written
-        // through at once (further back, the carried bytes are stored with the next group early enough)
+        // closer than 8 bytes, the next group reads bytes this group produced: the part of them that spills into the next
+        // word is written through at once (further back, the carried bytes are stored with the next group early enough)
         const bool wt = dsh != 0u && vop - s < 8u;
-#pragma unroll
-        for (int g = 0; g < MAXG; g++) {
-            if ((uint32_t)g >= G) break;                           // (uniform)
-            if ((uint32_t)g < myg) {
-                const uint32_t lo = far ? q[g] : ld(sp + 4u * g), hi = far ? q[g + 1] : ld(sp + 4u * g + 4u);
-                uint32_t x = simt::funnel_r(lo, hi, ssh);
-                const uint32_t rem = n - 4u * g;                   // bytes of this group: 4, or 1..4 in the last one
-                if (rem < 4u) x &= (1u << (8u * rem)) - 1u;
-                const uint32_t w = simt::funnel_l(c, x, dsh);
-                simt::sts_u32(ow, oword(l4, v4 + 4u * g), w);
-                if (rem > 4u) {
-                    if (wt) simt::sts_u32(ow, oword(l4, v4 + 4u * g + 4u), x >> (32u - dsh));
-                    c = x;
-                } else if (k + rem >= 4u) {                        // last group, word finished: what spilled over starts the next one
-                    acc = dsh ? x >> (32u - dsh) : 0u;
-                    if (k + rem > 4u) simt::sts_u32(ow, oword(l4, v4 + 4u * g + 4u), acc);
-                } else acc = w;
-            }
+        while (rem > 4) {
+            const uint32_t x = simt::funnel_r(ld(sp), ld(sp + 4), ssh);
+            simt::sts_u32(ow, oword(l4, v4), simt::funnel_l(c, x, dsh));
+            if (wt) simt::sts_u32(ow, oword(l4, v4 + 4), x >> (32u - dsh));
+            c = x; sp += 4; v4 += 4; rem -= 4;
         }
-        if (on) vop += n;
+        {
+            uint32_t x = simt::funnel_r(ld(sp), ld(sp + 4), ssh);
+            if (rem < 4) x &= (1u << (8u * rem)) - 1u;
+            const uint32_t carried = dsh ? c >> (32u - dsh) : 0u;
+            const uint32_t w = carried | (x << dsh);
+            simt::sts_u32(ow, oword(l4, v4), w);
+            if (k + rem >= 4) {
+                acc = dsh ? x >> (32u - dsh) : 0u;
+                if (k + rem > 4) simt::sts_u32(ow, oword(l4, v4 + 4), acc);
+            } else acc = w;
+        }
+        vop += n;
     };
     // one byte (overlapping matches closer than 4 bytes; sources that straddle the ring's valid range)
     auto append_byte = [&](uint32_t b) {
@@ -362,11 +352,7 @@ SIMT_DEV void lpb_decode_warp(LpbShared<GEO>* sh, const LpbBatch& a, uint32_t* c
             const uint32_t anym = simt::ballot(FULL, mcan), mixed = simt::ballot(FULL, mcan && !ring8);
             if (anym) {
                 if (!mixed) { if (mcan) { append(LpbKind<1>(), m_s, m_n); ip = m_q; phase = 0; } }
-                else {
-                    const uint32_t maxn = simt::reduce_max(FULL, mcan ? m_n : 0u);
-                    append_mixed(mcan, m_s, m_n, m_rmin, (maxn + 3u) >> 2);
-                    if (mcan) { ip = m_q; phase = 0; }
-                }
+                else if (mcan) { append_mixed(m_s, m_n, m_rmin); ip = m_q; phase = 0; }
             }
           }
           if (go) {
