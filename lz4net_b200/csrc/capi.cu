@@ -123,7 +123,7 @@ struct lz4b200_ctx {
     int64_t launches = 0;
     std::mutex mu;
 
-    uint32_t* counter() { uint32_t* c = counters + next_counter; next_counter = (next_counter + 2) % NCOUNTER; return c; }   // pairs: [block counter, decoder pick]
+    uint32_t* counter() { uint32_t* c = counters + next_counter; next_counter = (next_counter + 4) % NCOUNTER; return c; }   // fours: [block counter, decoder pick, two more counters]
 };
 
 namespace {

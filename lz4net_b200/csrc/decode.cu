@@ -103,7 +103,6 @@ static cudaError_t launch_g(const BatchArgs& a, bool known, bool staged, uint32_
 typedef LpbGeom<128, 256, 32, 0, 2> LpbDefault;
 // Warps per CTA: what 227 KiB of shared memory hold rings for, rounded DOWN to a multiple of four -- ptxas budgets registers
 // for the block size rounded up to 128 threads (17 warps were given the 96 registers of 20 and spilled the copy loops).
-template <int IN_, int OUT_, int MAXRUN_, int DEPTH_, int SEQS_> struct LpbGeom;
 template <class GEO> constexpr int lpb_warps() { return (int)((232448 / sizeof(LpbShared<GEO>)) / 4 * 4) > 0 ? (int)((232448 / sizeof(LpbShared<GEO>)) / 4 * 4) : 1; }
 
 template <bool KNOWN, class GEO>
@@ -154,24 +153,35 @@ cudaError_t launch_decode(const BatchArgs& a, bool known_len, int lanes, uint32_
                           const DeviceInfo& dev, cudaStream_t stream, int64_t* launches)
 {
     if (a.n_blocks <= 0) return cudaSuccess;
-    cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), stream);
+    cudaError_t e = cudaMemsetAsync(counter, 0, 4 * sizeof(uint32_t), stream);     // [block counter, decoder pick, two more block counters]
     if (e != cudaSuccess) return e;
     if (launches) ++*launches;
     if (lanes == 0) {
         // auto: pick on the device, enqueue the four candidates (three of them return at once: ~3 us of GPU time each)
-        int* pick = (int*)(counter + 1);             // (the context hands out counters in pairs: [block counter, pick])
+        int* pick = (int*)(counter + 1);             // (the context hands out counters in fours: [block counter, pick, two more counters])
         lz4_decode_pick_kernel<<<1, 256, 0, stream>>>(a.src_len, a.dst_cap, a.n_blocks, pick);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if (launches) *launches += 2;
         if ((e = launch_g<32>(a, known_len, false, counter, dev, stream, pick, 32)) != cudaSuccess) return e;
         if ((e = launch_g<16>(a, known_len, false, counter, dev, stream, pick, 16)) != cudaSuccess) return e;
-        const bool lpb104 = lpb_pays(a.n_blocks, dev, false), lpb108 = lpb_pays(a.n_blocks, dev, true);
-        if (launches) *launches += 2 + (lpb104 ? 1 : 0) + (lpb108 ? 0 : 1) + (lpb104 ? 0 : 1);
-        if (lpb104) {
-            e = known_len ? launch_lpb<true, LpbDefault>(a, counter, dev, stream, pick, lpb108 ? 1 : 0) : launch_lpb<false, LpbDefault>(a, counter, dev, stream, pick, lpb108 ? 1 : 0);
+        // Sequence-dense classes.  The lane-per-block decoder works a batch off in waves of one block per lane; it gets the
+        // whole waves, the group kernels the rest (a last wave that is 46 % full, as in a 262 144-block batch, costs the
+        // token-dense class a quarter of its rate).  Batches below one wave: lpb_pays().
+        const int64_t wave = (int64_t)dev.num_sms * 32 * lpb_warps<LpbDefault>();
+        const int64_t head = a.n_blocks >= wave ? a.n_blocks / wave * wave : (lpb_pays(a.n_blocks, dev, false) ? a.n_blocks : 0);
+        const bool head108 = a.n_blocks >= wave || lpb_pays(a.n_blocks, dev, true);
+        if (head > 0) {
+            BatchArgs h = a; h.n_blocks = (int32_t)head;
+            if (launches) ++*launches;
+            e = known_len ? launch_lpb<true, LpbDefault>(h, counter, dev, stream, pick, head108 ? 1 : 0) : launch_lpb<false, LpbDefault>(h, counter, dev, stream, pick, head108 ? 1 : 0);
             if (e != cudaSuccess) return e;
         }
-        if (!lpb108 && (e = launch_g<8>(a, known_len, true, counter, dev, stream, pick, 108)) != cudaSuccess) return e;
-        if (!lpb104 && (e = launch_g<4>(a, known_len, true, counter, dev, stream, pick, 104)) != cudaSuccess) return e;
+        // the rest of the batch (or all of it) for the group kernels; class 108 also takes the head when the lanes did not
+        uint32_t* tc = counter + 2;
+        const int64_t skip104 = head, skip108 = head108 ? head : 0;
+        auto tail = [&](int64_t skip) { BatchArgs r = a; r.src_off += skip; r.src_len += skip; r.dst_off += skip; r.dst_cap += skip; r.out_len += skip; r.n_blocks = (int32_t)(a.n_blocks - skip); return r; };
+        if (a.n_blocks - skip108 > 0) { if (launches) ++*launches; if ((e = launch_g<8>(tail(skip108), known_len, true, tc, dev, stream, pick, 108)) != cudaSuccess) return e; }
+        if (a.n_blocks - skip104 > 0) { if (launches) ++*launches; if ((e = launch_g<4>(tail(skip104), known_len, true, tc + 1, dev, stream, pick, 104)) != cudaSuccess) return e; }
         return cudaSuccess;
     }
     const bool staged = lanes >= 100;            // lanes = 100 + G selects the output-staged variant

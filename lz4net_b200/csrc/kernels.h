@@ -16,7 +16,7 @@ struct DeviceInfo { int num_sms; int smem_per_sm; int smem_optin; };
 // All launchers are asynchronous on `stream`; `counter` is a device uint32 the launcher zeroes itself (dynamic
 // block hand-out).  They return the launch error (cudaSuccess on success) and add to *launches.
 // lanes_per_block: 32 | 16 | 8 | 4 (+100 = output-staged), 1 | 2 = the lane-per-block decoder, 0 = chosen on the device from
-// the batch's compression ratio (`counter` must then be followed by one more int32 the library owns).
+// the batch's compression ratio.  `counter` points at FOUR device words the launcher owns (block counter, pick, two more counters).
 int         decode_lanes_for_ratio(double ratio);
 cudaError_t launch_decode(const BatchArgs& a, bool known_len, int lanes_per_block, uint32_t* counter,
                           const DeviceInfo& dev, cudaStream_t stream, int64_t* launches);
