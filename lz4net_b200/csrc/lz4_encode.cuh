@@ -349,6 +349,7 @@ SIMT_DEV int encode_block_t(void* table, const uint8_t* src, int n, uint8_t* dst
         int pfpos = 0;
         for (;;) {
             int ip = 0, ref = 0; bool again = false, have = false, finished = false;
+            InWords::Raw pre_ra{0, 0, 0}, pre_rr{0, 0, 0}; bool pre = false;   // the first count words of a probe hit, already in flight
             if (probe_first) {
                 // The post-match table operations (:519-531 / :739-751) on their own, warp-uniform: in token-dense data
                 // the probe at ip usually hits (a zero-literal sequence) and a whole round would be wasted work.
@@ -358,11 +359,19 @@ SIMT_DEV int encode_block_t(void* table, const uint8_t* src, int n, uint8_t* dst
                 const uint32_t h2 = (v2 * 2654435761u) >> HSHIFT, h = (vi * 2654435761u) >> HSHIFT;
                 const int t = (h == h2) ? p2 : T.get(h);
                 const uint32_t w = in.at(t);
+                // the words the match count will compare if the probe hits (it usually does here): requested together with the
+                // candidate word, so the count does not start another memory round trip after the verdict
+                {
+                    const int a = mp + 4 + 4 * lane;
+                    int room = matchlimit - a; room = room < 0 ? 0 : (room > 4 ? 4 : room);
+                    pre_ra = in.raw<LDP>(room > 0 ? a : 0); pre_rr = in.raw<LDP>(room > 0 ? t + 4 + 4 * lane : 0);
+                    pre = true;
+                }
                 simt::syncwarp(FULL);                              // every lane has read the bucket
                 if (lane == 0) { T.put(h2, p2); T.put(h, mp); }
                 simt::syncwarp(FULL);
                 if ((!GENERAL || t > mp - 65536) && w == vi) { ip = mp; ref = t; again = true; have = true; }
-                else { org = mp + 1 - 3; A0 = 67; fused = false; wide = false; }
+                else { org = mp + 1 - 3; A0 = 67; fused = false; wide = false; pre = false; }
             }
             while (!have) {
                 RoundOut r;
@@ -397,7 +406,7 @@ SIMT_DEV int encode_block_t(void* table, const uint8_t* src, int n, uint8_t* dst
             {
                 const int a = mp + 4 * lane;
                 int room = matchlimit - a; room = room < 0 ? 0 : (room > 4 ? 4 : room);
-                const InWords::Raw ra = in.raw<LDP>(room > 0 ? a : 0), rr = in.raw<LDP>(room > 0 ? mr + 4 * lane : 0);
+                const InWords::Raw ra = pre ? pre_ra : in.raw<LDP>(room > 0 ? a : 0), rr = pre ? pre_rr : in.raw<LDP>(room > 0 ? mr + 4 * lane : 0);
                 if (ip > anchor) {                                  // (never after a zero-literal probe hit: ip == anchor)
                     const int k = lane + 1;
                     const bool okb = ip - k >= anchor && ref - k >= 0;
