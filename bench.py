@@ -559,7 +559,7 @@ def main():
     except Exception:
         pass
     tsrc = "static: profiles/ncu_traffic.json (ncu --set full, bytes per block x blocks per launch), not measured in this run"
-    roof_dec = {"kernel": "lz4_decode_kernel", "bound": "hbm", "achieved": round(alg / t_dec / GB, 1), "peak": peak_hbm, "unit": "GB/s",
+    roof_dec = {"kernel": "lz4_decode_lpb_kernel (whole waves of the batch) + lz4_decode_kernel<8> (the rest), as picked on the device", "bound": "hbm", "achieved": round(alg / t_dec / GB, 1), "peak": peak_hbm, "unit": "GB/s",
                 "frac": round(alg / t_dec / GB / peak_hbm, 4), "traffic": traffic_dec, "traffic_source": tsrc, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": int(alg / nw), "launch_ms": round(t_dec / nw * 1e3, 3)}
     roof_enc = {"kernel": "lz4_encode_fast_kernel", "bound": "hbm", "achieved": round(alg / t_enc / GB, 1), "peak": peak_hbm, "unit": "GB/s",

@@ -9,7 +9,8 @@ echo "=== bench (default) ==="
 python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; tail -c 5000 gpurun_out/bench_$TAG.json; tail -5 gpurun_out/bench_$TAG.err
 echo "=== bench --impl reference ==="
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2> gpurun_out/bench_ref_$TAG.err; cat gpurun_out/bench_ref_$TAG.json; tail -3 gpurun_out/bench_ref_$TAG.err
-SMALL="--blocks 131072 --steps 2 --warmup 1 --no-sweep --no-hc --no-cpu --no-e2e"
+# 151552 blocks = two whole waves of the lane-per-block decoder: that kernel decodes every block of the launch
+SMALL="--blocks 151552 --steps 2 --warmup 1 --no-sweep --no-hc --no-cpu --no-e2e --no-stream"
 echo "=== ncu launch list ==="
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py $SMALL > gpurun_out/ncu_launch_$TAG.log 2>&1
 grep -c lz4 gpurun_out/launches_$TAG.csv
