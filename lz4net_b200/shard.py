@@ -106,26 +106,68 @@ def _all_gather_i64(value: int, device):
 
 
 def encode_stream_sharded(raw_root, n_blocks: int, block_size: int, encode_local, rank: int, world: int, root: int = 0,
-                          device=None):
+                          device=None, pieces: int = 4):
     """raw_root: uint8[n_blocks * block_size] on the root (ignored elsewhere; the last block may not be short).
-    encode_local(shard_bytes, m_blocks) -> (packed uint8[...], lens int32[m_blocks]) for this rank's m_blocks blocks.
+    encode_local(shard_bytes, m_blocks) -> (packed uint8[...], lens int32[m_blocks]) for m_blocks blocks.
     Returns on the root (lens int32[n_blocks], offsets int64[n_blocks + 1], packed uint8[total]) in stream order,
-    (None, None, None) elsewhere."""
+    (None, None, None) elsewhere.
+
+    Every rank's block range is cut into `pieces` sub-ranges; all transfers are posted up front and a piece is encoded as
+    soon as it has arrived, so the scatter of piece p+1 (NCCL's stream) overlaps the encode of piece p (the compute
+    stream): the root's NVLink egress and the kernels work at the same time instead of one after the other."""
     import torch
     import torch.distributed as dist
     dev = device if device is not None else (raw_root.device if raw_root is not None else "cpu")
     blk = [strong_range(r, world, n_blocks) for r in range(world)]
     like = torch.empty(0, dtype=torch.uint8, device=dev)
-    mine = scatter_ranges(raw_root, [(a * block_size, b * block_size) for a, b in blk], rank, root, like=like)
-    m = blk[rank][1] - blk[rank][0]
-    packed, lens = encode_local(mine, m) if m else (torch.empty(0, dtype=torch.uint8, device=dev), torch.empty(0, dtype=torch.int32, device=dev))
+    a, b = blk[rank]
+    m = b - a
+    pieces = max(1, min(pieces, m)) if m else 1
+    def sub(r, p, k):                                           # block sub-range p of k of rank r
+        lo, hi = blk[r]; n = hi - lo
+        return lo + n * p // k, lo + n * (p + 1) // k
+    works, bufs = [], []
+    for p in range(pieces):
+        if rank == root:
+            ops = []
+            for r in range(world):
+                if r == root:
+                    continue
+                k = max(1, min(pieces, blk[r][1] - blk[r][0])) if blk[r][1] > blk[r][0] else 1
+                if p < k:
+                    lo, hi = sub(r, p, k)
+                    if hi > lo:
+                        ops.append(dist.P2POp(dist.isend, raw_root[lo * block_size: hi * block_size], r))
+            works.append(dist.batch_isend_irecv(ops) if ops else [])
+            lo, hi = sub(root, p, pieces) if m else (0, 0)
+            bufs.append(raw_root[lo * block_size: hi * block_size])
+        else:
+            lo, hi = sub(rank, p, pieces) if m else (0, 0)
+            buf = torch.empty((hi - lo) * block_size, dtype=torch.uint8, device=dev)
+            works.append(dist.batch_isend_irecv([dist.P2POp(dist.irecv, buf, root)]) if hi > lo else [])
+            bufs.append(buf)
+    packed_parts, lens_parts = [], []
+    for p in range(pieces):
+        if rank != root:
+            for w in works[p]:
+                w.wait()
+        lo, hi = sub(rank, p, pieces) if m else (0, 0)
+        if hi > lo:
+            pk, ln = encode_local(bufs[p], hi - lo)
+            packed_parts.append(pk); lens_parts.append(ln)
+    if rank == root:
+        for ws in works:
+            for w in ws:
+                w.wait()
+    packed = torch.cat(packed_parts) if len(packed_parts) > 1 else (packed_parts[0] if packed_parts else like)
+    lens = torch.cat(lens_parts) if len(lens_parts) > 1 else (lens_parts[0] if lens_parts else torch.empty(0, dtype=torch.int32, device=dev))
     total = int(lens.to(torch.int64).sum().item()) if m else 0
     totals = _all_gather_i64(total, dev)                        # every rank's payload size: the only metadata exchanged
     pay = [(sum(totals[:r]), sum(totals[:r + 1])) for r in range(world)]
     out = torch.empty(sum(totals), dtype=torch.uint8, device=dev) if rank == root else None
     out = gather_ranges(packed, pay, rank, root, out)
     lens_all = torch.empty(n_blocks * 4, dtype=torch.uint8, device=dev) if rank == root else None
-    lens_all = gather_ranges(lens.contiguous().view(torch.uint8) if m else like, [(a * 4, b * 4) for a, b in blk], rank, root, lens_all)
+    lens_all = gather_ranges(lens.contiguous().view(torch.uint8) if m else like, [(x * 4, y * 4) for x, y in blk], rank, root, lens_all)
     if rank != root:
         return None, None, None
     lens_i = lens_all.view(torch.int32)
@@ -172,7 +214,7 @@ def gpu_codec(ctx, block_size: int, hc: bool = False):
         off = torch.zeros(m + 1, dtype=torch.int64, device=raw.device)
         packed = torch.empty(m * slot, dtype=torch.uint8, device=raw.device)
         batch.compact(ctx, slots, do, lens, packed, off)
-        torch.cuda.synchronize()
+        torch.cuda.current_stream().synchronize()               # (this stream only: transfers of later pieces keep running)
         assert int((lens <= 0).sum()) == 0, "encode failed"
         return packed[: int(off[-1].item())], lens
 
@@ -183,7 +225,7 @@ def gpu_codec(ctx, block_size: int, hc: bool = False):
         out = torch.empty(m * block_size, dtype=torch.uint8, device=packed.device)
         used = torch.zeros(m, dtype=torch.int32, device=packed.device)
         batch.decode(ctx, packed, off[:-1].contiguous(), lens, out, so, sl, used, known=True)
-        torch.cuda.synchronize()
+        torch.cuda.current_stream().synchronize()
         assert torch.equal(used, lens), "decode rejected a stream"
         return out
 
