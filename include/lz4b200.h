@@ -136,6 +136,12 @@ int lz4b200_unwrap_batch(lz4b200_ctx* ctx, const void* src, const int64_t* src_o
 int lz4b200_host_register(void* ptr, int64_t bytes);
 int lz4b200_host_unregister(void* ptr);
 
+/* ---- one stream, several GPUs of one node (BASELINE configs[3]; lz4net_b200/shard.py StreamWindow) --------------------
+ * Asynchronous copy between device buffers of two GPUs (either side may be memory another process exported with CUDA
+ * IPC), ordered on `stream` of the CURRENT device, executed by the copy engines over NVLink -- it overlaps codec kernels,
+ * which a send/recv kernel of a communication library does not.  Enables peer access on first use. */
+int lz4b200_peer_copy(void* dst, const void* src, int64_t bytes, void* stream);
+
 /* ---- synthetic workload generator (bench/test utility; device memory) ----------------------------------------
  * Fills n_blocks * block_size bytes at dst with entropy class cls (0 E0, 1 E50, 2 E100, 3 ETEXT), block index
  * first_block + i, exactly as lz4net_b200/synth.py defines them. */

@@ -632,6 +632,30 @@ int lz4b200_host_unregister(void* ptr)
     return LZ4B200_OK;
 }
 
+int lz4b200_peer_copy(void* dst, const void* src, int64_t bytes, void* stream)
+{
+    if (bytes < 0 || (bytes && (!dst || !src))) return fail(LZ4B200_E_ARG, "bad argument");
+    if (!bytes) return LZ4B200_OK;
+    int cur = 0, dev[2];
+    CU(cudaGetDevice(&cur));
+    const void* ends[2] = {dst, src};
+    for (int k = 0; k < 2; k++) {
+        cudaPointerAttributes at{};
+        CU(cudaPointerGetAttributes(&at, ends[k]));
+        if (at.type != cudaMemoryTypeDevice) return fail(LZ4B200_E_ARG, "lz4b200_peer_copy: both buffers must be device memory");
+        dev[k] = at.device;
+    }
+    for (int k = 0; k < 2; k++) {                                // both directions of the pair, once
+        CU(cudaSetDevice(dev[k]));
+        cudaError_t e = cudaDeviceEnablePeerAccess(dev[1 - k], 0);
+        (void)cudaGetLastError();
+        if (dev[0] != dev[1] && e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaSetDevice(cur); return cuda_fail(e, "cudaDeviceEnablePeerAccess"); }
+    }
+    CU(cudaSetDevice(cur));
+    CU(cudaMemcpyPeerAsync(dst, dev[0], src, dev[1], (size_t)bytes, (cudaStream_t)stream));   // a copy-engine transfer
+    return LZ4B200_OK;
+}
+
 int lz4b200_compress_limitedOutput(const char* s, char* d, int isize, int cap) { return single(s, d, isize, cap, 0); }
 int lz4b200_compressHC_limitedOutput(const char* s, char* d, int isize, int cap) { return single(s, d, isize, cap, 1); }
 int lz4b200_uncompress(const char* s, char* d, int isize, int osize) { return single(s, d, isize, osize, 2); }

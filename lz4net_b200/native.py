@@ -43,6 +43,7 @@ SIGNATURES = {
     "lz4b200_wrap_batch": (_I, [_P, _P, _P, _P, _I, _P, _P, _P, _P, C.c_int32]),
     "lz4b200_unwrap_batch": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int32]),
     "lz4b200_host_register": (_I, [_P, _L]),
+    "lz4b200_peer_copy": (_I, [_P, _P, _L, _P]),
     "lz4b200_host_unregister": (_I, [_P]),
     "lz4b200_synth_fill": (_I, [_P, _P, _L, C.c_int32, _I, _U64, _L, _P]),
     "lz4b200_set_option": (_I, [_P, C.c_char_p, _L]),

@@ -105,16 +105,31 @@ def _all_gather_i64(value: int, device):
     return [int(t.item()) for t in out]
 
 
+def _post(op, tensor, peer):
+    """One point-to-point transfer as its own group (its own kernel on the communicator's stream, so transfers posted one
+    after the other run one after the other); returns the work handles."""
+    import torch.distributed as dist
+    return dist.batch_isend_irecv([dist.P2POp(op, tensor, peer)])
+
+
+def _wait(works):
+    for w in works:
+        w.wait()
+
+
 def encode_stream_sharded(raw_root, n_blocks: int, block_size: int, encode_local, rank: int, world: int, root: int = 0,
-                          device=None, pieces: int = 4):
+                          device=None, pieces: int = 1):
     """raw_root: uint8[n_blocks * block_size] on the root (ignored elsewhere; the last block may not be short).
     encode_local(shard_bytes, m_blocks) -> (packed uint8[...], lens int32[m_blocks]) for m_blocks blocks.
     Returns on the root (lens int32[n_blocks], offsets int64[n_blocks + 1], packed uint8[total]) in stream order,
     (None, None, None) elsewhere.
 
-    Every rank's block range is cut into `pieces` sub-ranges; all transfers are posted up front and a piece is encoded as
-    soon as it has arrived, so the scatter of piece p+1 (NCCL's stream) overlaps the encode of piece p (the compute
-    stream): the root's NVLink egress and the kernels work at the same time instead of one after the other."""
+    Every rank's block range can be cut into `pieces` sub-ranges (all transfers posted up front, a piece encoded as soon
+    as it has arrived).  Measured on 2 and 4 B200s (tools/stream_ab.py) that buys nothing: a point-to-point transfer is a
+    KERNEL of the communication library, and it is not scheduled while the persistent encode kernel holds every SM's
+    shared memory -- the pieces arrive back to back before the first encode or after the last one.  (Sending rank 1 its
+    range first, then rank 2's, ... is worse for the same reason: 133 instead of 191 GB/s at 4 GPUs.)  The transfers that
+    do overlap the kernels are the copy engines' -- StreamWindow below."""
     import torch
     import torch.distributed as dist
     dev = device if device is not None else (raw_root.device if raw_root is not None else "cpu")
@@ -178,34 +193,244 @@ def encode_stream_sharded(raw_root, n_blocks: int, block_size: int, encode_local
 
 def decode_stream_sharded(packed_root, lens_root, n_blocks: int, block_size: int, decode_local, rank: int, world: int,
                           root: int = 0, device=None):
-    """Mirror image: packed_root / lens_root (int32[n_blocks]) on the root; decode_local(packed, lens, m_blocks) ->
-    uint8[m_blocks * block_size].  Returns the raw stream on the root, None elsewhere."""
+    """Mirror image: packed_root / lens_root (int32[n_blocks]) on the root; decode_local(packed, lens, m_blocks, out=None)
+    -> uint8[m_blocks * block_size] (written into `out` when given).  Returns the raw stream on the root, None elsewhere.
+    Staggered like the encode: rank r gets its lengths and its payload before rank r+1 does, and its decoded blocks cross
+    back (the root's ingress: the long leg) while the later ranks still receive and decode."""
     import torch
     import torch.distributed as dist
     dev = device if device is not None else (packed_root.device if packed_root is not None else "cpu")
     blk = [strong_range(r, world, n_blocks) for r in range(world)]
-    like = torch.empty(0, dtype=torch.uint8, device=dev)
-    lens = torch.empty(n_blocks, dtype=torch.int32, device=dev)
-    if rank == root:
-        lens.copy_(lens_root)
-    dist.broadcast(lens, src=root)                               # 4 bytes per block: everybody derives the payload ranges
+    a, b = blk[rank]
+    m = b - a
+    if rank != root:
+        if m:
+            lens = torch.empty(m, dtype=torch.int32, device=dev)
+            _wait(_post(dist.irecv, lens, root))
+            mine = torch.empty(int(lens.to(torch.int64).sum().item()), dtype=torch.uint8, device=dev)
+            _wait(_post(dist.irecv, mine, root))
+            raw = decode_local(mine, lens, m)
+            _wait(_post(dist.isend, raw, root))
+        return None
+    lens = lens_root.to(torch.int32).contiguous()
     off = torch.zeros(n_blocks + 1, dtype=torch.int64, device=dev)
     off[1:] = torch.cumsum(lens.to(torch.int64), 0)
-    offs = off.tolist()
-    pay = [(offs[a], offs[b]) for a, b in blk]
-    mine = scatter_ranges(packed_root, pay, rank, root, like=like)
-    a, b = blk[rank]
-    raw = decode_local(mine, lens[a:b].contiguous(), b - a) if b > a else like
-    out = torch.empty(n_blocks * block_size, dtype=torch.uint8, device=dev) if rank == root else None
-    return gather_ranges(raw, [(x * block_size, y * block_size) for x, y in blk], rank, root, out)
+    edges = off[torch.tensor([x for ab in blk for x in ab], dtype=torch.int64, device=dev)].tolist()   # 2 per rank, not n_blocks
+    works = []
+    for r in range(world):
+        lo, hi = blk[r]
+        if r != root and hi > lo:
+            works += _post(dist.isend, lens[lo:hi], r)
+            works += _post(dist.isend, packed_root[edges[2 * r]: edges[2 * r + 1]], r)
+    out = torch.empty(n_blocks * block_size, dtype=torch.uint8, device=dev)
+    for r in range(world):                                       # posted before the root's own decode: they fill as peers finish
+        lo, hi = blk[r]
+        if r != root and hi > lo:
+            works += _post(dist.irecv, out[lo * block_size: hi * block_size], r)
+    if m:
+        decode_local(packed_root[edges[2 * root]: edges[2 * root + 1]], lens[a:b], m, out=out[a * block_size: b * block_size])
+    _wait(works)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# The same job over peer memory (NVLink 5 / NVSwitch, CUDA IPC): the stream's buffers live in a WINDOW on the root that
+# every rank has mapped, and the peers move their ranges themselves with device-to-device copies between the window and
+# local buffers.  Those copies run on the copy engines, not on SMs, so -- unlike a send/recv kernel -- they do overlap the
+# persistent codec kernels: a rank pulls piece p+1 and pushes piece p-1 while piece p is in the kernel.  The only
+# collective is a barrier on either side (plus an all-gather of one payload size per rank on the encode side).
+# ----------------------------------------------------------------------------------------------------------------------
+class StreamWindow:
+    """Root-resident buffers of one stream of n_blocks x block_size bytes, mapped by every rank:
+    raw uint8[n_blocks * block_size], packed uint8[n_blocks * bound], lens int32[n_blocks], off int64[n_blocks + 1].
+    Created collectively, once (the mapping costs milliseconds: like a communicator, it is set up outside the data path)
+    and reused for any number of encode / decode calls.  GPU only (one process per GPU on one node)."""
+
+    def __init__(self, n_blocks: int, block_size: int, rank: int, world: int, root: int = 0, device=None, bound_per_block: int = 0):
+        import torch
+        import torch.distributed as dist
+        from torch.multiprocessing.reductions import reduce_tensor
+        self.n_blocks, self.block_size, self.rank, self.world, self.root = n_blocks, block_size, rank, world, root
+        self.bound = bound_per_block or (block_size + block_size // 255 + 16)
+        self.device = device
+        names = ("raw", "packed", "lens", "off")
+        handles = [None]
+        if rank == root:
+            self.raw = torch.empty(n_blocks * block_size, dtype=torch.uint8, device=device)
+            self.packed = torch.empty(n_blocks * self.bound, dtype=torch.uint8, device=device)
+            self.lens = torch.zeros(n_blocks, dtype=torch.int32, device=device)
+            self.off = torch.zeros(n_blocks + 1, dtype=torch.int64, device=device)
+            torch.cuda.synchronize()
+            handles = [[reduce_tensor(getattr(self, k)) for k in names]]
+        dist.broadcast_object_list(handles, src=root)
+        if rank != root:
+            for k, (fn, a) in zip(names, handles[0]):
+                setattr(self, k, fn(*a))                         # a view of the root's memory (device = the root's index)
+            self.copy_in = torch.cuda.Stream(device=device)
+            self.copy_out = torch.cuda.Stream(device=device)
+        dist.barrier()
+
+    def close(self):
+        """Collective: the peers unmap the window, then the root lets go of it."""
+        import torch
+        import torch.distributed as dist
+        if self.rank != self.root:
+            for k in ("raw", "packed", "lens", "off"):
+                setattr(self, k, None)
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.ipc_collect()
+        if self.rank == self.root:
+            for k in ("raw", "packed", "lens", "off"):
+                setattr(self, k, None)
+
+    def ranges(self, pieces: int):
+        """This rank's block range cut into at most `pieces` sub-ranges."""
+        a, b = strong_range(self.rank, self.world, self.n_blocks)
+        k = max(1, min(pieces, b - a))
+        return [(a + (b - a) * p // k, a + (b - a) * (p + 1) // k) for p in range(k)] if b > a else []
+
+
+def _peer_copy(dst, src, stream):
+    """dst <- src between two GPUs, ordered on `stream` of this rank's device (a copy-engine transfer).  Not Tensor.copy_:
+    that one runs on the SOURCE device's current stream with an event hand-shake either side, which (measured) lets the
+    first kernel start only after the last queued pull."""
+    assert dst.is_contiguous() and src.is_contiguous() and dst.numel() * dst.element_size() == src.numel() * src.element_size()
+    from . import native
+    native.check(native.lib().lz4b200_peer_copy(dst.data_ptr(), src.data_ptr(), dst.numel() * dst.element_size(), stream.cuda_stream),
+                 "lz4b200_peer_copy")
+
+
+def _mark(trace, what, stream=None):
+    if trace is not None:
+        import torch
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(stream if stream is not None else torch.cuda.current_stream())
+        trace.append((what, ev))
+
+
+def _pull(win_slice, stream, trace=None):
+    """Window -> a new local buffer, on `stream`; returns (buffer, event)."""
+    import torch
+    buf = torch.empty(win_slice.numel(), dtype=win_slice.dtype, device=stream.device)
+    stream.wait_stream(torch.cuda.current_stream())              # (the buffer's previous life on the current stream is over)
+    _peer_copy(buf, win_slice, stream)
+    ev = torch.cuda.Event()
+    ev.record(stream)
+    buf.record_stream(stream)
+    _mark(trace, "pulled", stream)
+    return buf, ev
+
+
+def _push(win_slice, local, stream, trace=None):
+    """A local buffer -> the window, on `stream`, after everything queued so far on the current stream."""
+    import torch
+    stream.wait_stream(torch.cuda.current_stream())
+    _peer_copy(win_slice, local, stream)
+    local.record_stream(stream)
+    _mark(trace, "pushed", stream)
+
+
+def _halves(f):
+    """(launch, finish) of a codec function: its own two halves when it has them, else the whole call up front."""
+    if hasattr(f, "launch"):
+        return f.launch, f.finish
+    return (lambda *a, **k: f(*a, **k)), (lambda h: h)
+
+
+def encode_stream_window(win: "StreamWindow", encode_local, pieces: int = 4, trace=None):
+    """The raw stream is in win.raw on the root (complete before the call).  On return (all ranks) win.lens, win.off and
+    win.packed[:win.off[-1]] hold the encoded stream in stream order; the root gets (lens, off, packed) views.
+    A peer queues ALL its pulls and, behind each one's event, that piece's kernels, without touching the host in
+    between (a host read-back mid-way would queue behind the bulk transfers on the copy engines)."""
+    import torch
+    import torch.distributed as dist
+    bs, rank, root = win.block_size, win.rank, win.root
+    launch, finish = _halves(encode_local)
+    torch.cuda.synchronize()
+    dist.barrier()                                               # the root's raw bytes are in place
+    _mark(trace, "start")
+    rng = win.ranges(pieces)
+    hs = []
+    if rank == root:
+        for lo, hi in rng:
+            hs.append(launch(win.raw[lo * bs: hi * bs], hi - lo)); _mark(trace, "encoded")
+    else:
+        pulls = [_pull(win.raw[lo * bs: hi * bs], win.copy_in, trace) for lo, hi in rng]    # all queued: they run back to back
+        for (lo, hi), (buf, ev) in zip(rng, pulls):
+            torch.cuda.current_stream().wait_event(ev)
+            hs.append(launch(buf, hi - lo)); _mark(trace, "encoded")
+    torch.cuda.current_stream().synchronize()
+    parts = [finish(h) for h in hs]
+    total = sum(int(pk.numel()) for pk, _ in parts)
+    totals = _all_gather_i64(total, win.device)
+    pos = sum(totals[:rank])
+    for (lo, hi), (pk, ln) in zip(rng, parts):                   # own payloads and lengths into the window, in stream order
+        if rank == root:
+            win.packed[pos: pos + pk.numel()] = pk
+            win.lens[lo:hi] = ln
+        else:
+            _push(win.packed[pos: pos + pk.numel()], pk, win.copy_out, trace)
+            _push(win.lens[lo:hi], ln, win.copy_out)
+        pos += int(pk.numel())
+    torch.cuda.synchronize()
+    _mark(trace, "landed")
+    dist.barrier()                                               # everybody's bytes have landed
+    if rank != root:
+        return None, None, None
+    win.off[1:] = torch.cumsum(win.lens.to(torch.int64), 0)
+    return win.lens, win.off, win.packed[: sum(totals)]
+
+
+def decode_stream_window(win: "StreamWindow", decode_local, pieces: int = 4, trace=None):
+    """win.lens / win.off / win.packed hold an encoded stream on the root (as encode_stream_window leaves them); on return
+    win.raw holds the decoded stream (returned on the root).  A peer pulls piece p+1 and pushes piece p-1 while piece p
+    is in the kernel; everything is queued up front."""
+    import torch
+    import torch.distributed as dist
+    bs, rank, root = win.block_size, win.rank, win.root
+    launch, finish = _halves(decode_local)
+    torch.cuda.synchronize()
+    dist.barrier()
+    rng = win.ranges(pieces)
+    _mark(trace, "start")
+    hs = []
+    if rank == root and rng:
+        a, b = rng[0][0], rng[-1][1]
+        edge = win.off[torch.tensor([lo for lo, _ in rng] + [b], device=win.off.device)].tolist()
+        for i, (lo, hi) in enumerate(rng):
+            hs.append(launch(win.packed[edge[i]: edge[i + 1]], win.lens[lo:hi], hi - lo, out=win.raw[lo * bs: hi * bs]))
+            _mark(trace, "decoded")
+    elif rng:
+        a, b = rng[0][0], rng[-1][1]
+        off, _ = _pull(win.off[a: b + 1], win.copy_in)           # 8 bytes per block: where my payloads are
+        lens, ev = _pull(win.lens[a:b], win.copy_in)
+        ev.synchronize()
+        edge = off[torch.tensor([lo - a for lo, _ in rng] + [b - a], device=off.device)].tolist()
+        pulls = [_pull(win.packed[edge[i]: edge[i + 1]], win.copy_in, trace) for i in range(len(rng))]
+        for i, (lo, hi) in enumerate(rng):
+            torch.cuda.current_stream().wait_event(pulls[i][1])
+            h = launch(pulls[i][0], lens[lo - a: hi - a], hi - lo)
+            _mark(trace, "decoded")
+            raw = h[0] if isinstance(h, tuple) else h
+            _push(win.raw[lo * bs: hi * bs], raw, win.copy_out, trace)
+            hs.append(h)
+    torch.cuda.synchronize()
+    for h in hs:
+        finish(h)
+    dist.barrier()
+    return win.raw if rank == root else None
 
 
 def gpu_codec(ctx, block_size: int, hc: bool = False):
-    """(encode_local, decode_local) on device tensors through the C ABI (lz4b200_encode_batch / compact / decode_batch)."""
+    """(encode_local, decode_local) on device tensors through the C ABI (lz4b200_encode_batch / compact / decode_batch).
+    Each also comes in two halves -- f.launch(...) queues the kernels on the current stream without touching the host,
+    f.finish(handle) is called after the stream has been synchronized -- so a caller can queue several pieces behind
+    their transfers and pay for one synchronization."""
     import torch
     from . import batch
 
-    def encode_local(raw, m):
+    def encode_launch(raw, m):
         slot = block_size + block_size // 255 + 16
         so, do, sl, dc = batch.uniform_layout(m, block_size, slot, raw.device)
         slots = torch.empty(m * slot, dtype=torch.uint8, device=raw.device)
@@ -214,19 +439,38 @@ def gpu_codec(ctx, block_size: int, hc: bool = False):
         off = torch.zeros(m + 1, dtype=torch.int64, device=raw.device)
         packed = torch.empty(m * slot, dtype=torch.uint8, device=raw.device)
         batch.compact(ctx, slots, do, lens, packed, off)
-        torch.cuda.current_stream().synchronize()               # (this stream only: transfers of later pieces keep running)
-        assert int((lens <= 0).sum()) == 0, "encode failed"
+        return packed, lens, off, (lens <= 0).sum()
+
+    def encode_finish(h):
+        packed, lens, off, bad = h
+        assert int(bad) == 0, "encode failed"
         return packed[: int(off[-1].item())], lens
 
-    def decode_local(packed, lens, m):
+    def encode_local(raw, m):
+        h = encode_launch(raw, m)
+        torch.cuda.current_stream().synchronize()               # (this stream only)
+        return encode_finish(h)
+
+    def decode_launch(packed, lens, m, out=None):
         off = torch.zeros(m + 1, dtype=torch.int64, device=packed.device)
         off[1:] = torch.cumsum(lens.to(torch.int64), 0)
         so, _, sl, _ = batch.uniform_layout(m, block_size, block_size, packed.device)
-        out = torch.empty(m * block_size, dtype=torch.uint8, device=packed.device)
+        if out is None:
+            out = torch.empty(m * block_size, dtype=torch.uint8, device=packed.device)
         used = torch.zeros(m, dtype=torch.int32, device=packed.device)
         batch.decode(ctx, packed, off[:-1].contiguous(), lens, out, so, sl, used, known=True)
-        torch.cuda.current_stream().synchronize()
-        assert torch.equal(used, lens), "decode rejected a stream"
+        return out, (used != lens).sum()
+
+    def decode_finish(h):
+        out, bad = h
+        assert int(bad) == 0, "decode rejected a stream"
         return out
 
+    def decode_local(packed, lens, m, out=None):
+        h = decode_launch(packed, lens, m, out)
+        torch.cuda.current_stream().synchronize()
+        return decode_finish(h)
+
+    encode_local.launch, encode_local.finish = encode_launch, encode_finish
+    decode_local.launch, decode_local.finish = decode_launch, decode_finish
     return encode_local, decode_local

@@ -38,7 +38,19 @@ def _worker(rank, world, port, n_blocks, out_dir):
     back = shard.decode_stream_sharded(packed, lens, n_blocks, bs, dec, rank, world, device=torch.device("cuda", rank))
     if rank == 0:
         assert torch.equal(back, raw)
+    # the same over peer memory (CUDA IPC window on the root, copy-engine transfers): same bytes
+    win = shard.StreamWindow(n_blocks, bs, rank, world, device=torch.device("cuda", rank))
+    if rank == 0:
+        win.raw.copy_(raw)
+    wl, wo, wp = shard.encode_stream_window(win, enc, pieces=3)
+    if rank == 0:
+        assert torch.equal(wl, lens) and torch.equal(wp, packed) and int(wo[-1]) == packed.numel()
+        win.raw.zero_()
+    wb = shard.decode_stream_window(win, dec, pieces=3)
+    if rank == 0:
+        assert torch.equal(wb, raw)
         open(os.path.join(out_dir, "ok"), "w").write("1")
+    win.close()
     dist.barrier()
     dist.destroy_process_group()
 

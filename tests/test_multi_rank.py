@@ -66,8 +66,8 @@ def _toy_codec(bs):
         lens = torch.tensor([max(1, int(torch.nonzero(b).max().item()) + 1 if bool(b.any()) else 1) for b in blocks], dtype=torch.int32)
         return torch.cat([b[:int(n)] for b, n in zip(blocks, lens)]), lens
 
-    def dec(packed, lens, m):
-        out = torch.zeros(m * bs, dtype=torch.uint8)
+    def dec(packed, lens, m, out=None):
+        out = torch.zeros(m * bs, dtype=torch.uint8) if out is None else out.zero_()
         p = 0
         for i, n in enumerate(lens.tolist()):
             out[i * bs:i * bs + n] = packed[p:p + n]; p += n
