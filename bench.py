@@ -397,7 +397,12 @@ def stream_section(ctx, args, rank, world, dev):
     torch.cuda.empty_cache()
     enc, dec = shard.gpu_codec(ctx, BLOCK)
     raw = None
-    win = shard.StreamWindow(nb, BLOCK, rank, world, device=dev) if world > 1 else None   # set up once, like the communicator
+    win, werr = None, None
+    if world > 1:                                               # set up once, like the communicator
+        try:
+            win = shard.StreamWindow(nb, BLOCK, rank, world, device=dev)
+        except RuntimeError as e:                               # (raised on every rank alike: peer memory not available here)
+            werr = str(e)[:300]
     if rank == 0:
         raw = win.raw if win is not None else torch.empty(nb * BLOCK, dtype=torch.uint8, device=dev)
         for b0 in range(0, nb, 65536):
@@ -425,8 +430,8 @@ def stream_section(ctx, args, rank, world, dev):
         best = (te, td)
     # ---- the same job over peer memory: the stream's buffers are a CUDA-IPC window on the root, the peers pull / push
     # their ranges with copy-engine transfers (lz4b200_peer_copy) that overlap the codec kernels piece by piece
-    wres = None
-    if world > 1:
+    wres = {"unavailable": werr} if werr else None
+    if win is not None:
         keep = raw.clone() if rank == 0 else None               # (the decode overwrites win.raw: compare against a copy)
         for it in range(2):
             torch.cuda.synchronize(); dist.barrier()
@@ -619,11 +624,18 @@ def main():
         rg = e2e_sequential(local, args.cls, min(nb_e, 4096), 2, 1, "registered")
         te, td, tp, tpg, trg = shard.reduce_max([r["t_enc"], r["t_dec"], pl["t_step"], pg["t_enc"] + pg["t_dec"], rg["t_enc"] + rg["t_dec"]], device="cuda")
         seq = r["bytes"] * world / (te + td) / GB; pip = r["bytes"] * world / tp / GB
+        mine_e2e = {"rank": rank, "numa_node": numa.get("numa_node"), "bound": numa.get("bound"),
+                    "sequential_gbs": round(r["bytes"] / (r["t_enc"] + r["t_dec"]) / GB, 2), "pipelined_gbs": round(r["bytes"] / pl["t_step"] / GB, 2)}
+        per_rank = [None] * world
+        if world > 1:
+            dist.all_gather_object(per_rank, mine_e2e)
+        else:
+            per_rank = [mine_e2e]
         e2e = {"value": round(max(seq, pip), 3), "unit": "GB/s", "h2d_bytes_per_step": int(r["h2d"]), "d2h_bytes_per_step": int(r["d2h"]),
                "sequential_gbs": round(seq, 3), "pipelined_gbs": round(pip, 3),
                "encode_gbs": round(r["bytes"] * world / te / GB, 3), "decode_gbs": round(r["bytes"] * world / td / GB, 3),
                "pageable_gbs": round(pg["bytes"] * world / tpg / GB, 3), "registered_gbs": round(rg["bytes"] * world / trg / GB, 3),
-               "numa": numa,
+               "numa": numa, "per_rank": per_rank,
                "sample": f"{nb_e} x 64 KiB blocks per GPU through lz4b200_encode_batch_packed + lz4b200_decode_batch (MEM_HOST), wall clock, every copy inside the calls. "
                          "value = the better of: sequential (one caller thread: encode, then decode) and pipelined (two caller threads, a context each: the encode of step i+1 "
                          "overlaps the decode of step i, both PCIe directions busy). pinned host memory; pageable_gbs / registered_gbs: the sequential form from plain "

@@ -254,21 +254,37 @@ class StreamWindow:
         self.bound = bound_per_block or (block_size + block_size // 255 + 16)
         self.device = device
         names = ("raw", "packed", "lens", "off")
-        handles = [None]
-        if rank == root:
-            self.raw = torch.empty(n_blocks * block_size, dtype=torch.uint8, device=device)
-            self.packed = torch.empty(n_blocks * self.bound, dtype=torch.uint8, device=device)
-            self.lens = torch.zeros(n_blocks, dtype=torch.int32, device=device)
-            self.off = torch.zeros(n_blocks + 1, dtype=torch.int64, device=device)
-            torch.cuda.synchronize()
-            handles = [[reduce_tensor(getattr(self, k)) for k in names]]
+        handles, err = [None], None
+        if rank == root:                                         # a failure on one rank must not leave the others waiting
+            try:
+                self.raw = torch.empty(n_blocks * block_size, dtype=torch.uint8, device=device)
+                self.packed = torch.empty(n_blocks * self.bound, dtype=torch.uint8, device=device)
+                self.lens = torch.zeros(n_blocks, dtype=torch.int32, device=device)
+                self.off = torch.zeros(n_blocks + 1, dtype=torch.int64, device=device)
+                if not self.raw.is_cuda:
+                    raise RuntimeError("StreamWindow needs CUDA device memory")
+                torch.cuda.synchronize()
+                handles = [[reduce_tensor(getattr(self, k)) for k in names]]
+            except Exception as e:                               # noqa: BLE001 -- reported to every rank below
+                handles = [("error", f"{type(e).__name__}: {e}"[:300])]
         dist.broadcast_object_list(handles, src=root)
-        if rank != root:
-            for k, (fn, a) in zip(names, handles[0]):
-                setattr(self, k, fn(*a))                         # a view of the root's memory (device = the root's index)
-            self.copy_in = torch.cuda.Stream(device=device)
-            self.copy_out = torch.cuda.Stream(device=device)
-        dist.barrier()
+        if isinstance(handles[0], tuple) and handles[0][0] == "error":
+            err = handles[0][1]
+        elif rank != root:
+            try:
+                for k, (fn, a) in zip(names, handles[0]):
+                    setattr(self, k, fn(*a))                     # a view of the root's memory (device = the root's index)
+                self.copy_in = torch.cuda.Stream(device=device)
+                self.copy_out = torch.cuda.Stream(device=device)
+            except Exception as e:                               # noqa: BLE001
+                err = f"rank {rank}: {type(e).__name__}: {e}"[:300]
+        errs = [None] * world
+        dist.all_gather_object(errs, err)
+        errs = [e for e in errs if e]
+        if errs:
+            for k in names:
+                setattr(self, k, None)
+            raise RuntimeError("StreamWindow could not be set up: " + errs[0])
 
     def close(self):
         """Collective: the peers unmap the window, then the root lets go of it."""

@@ -103,3 +103,21 @@ def test_stream_scatter_encode_gather_gloo(tmp_path, world, n_blocks):
     """More ranks than blocks, uneven splits, one block: order and bytes are those of the single-rank result."""
     mp.spawn(_stream_worker, args=(world, _free_port(), n_blocks, 64, str(tmp_path)), nprocs=world, join=True)
     assert (tmp_path / "ok").exists()
+
+
+def _window_refused_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        shard.StreamWindow(4, 64, rank, world)                     # no CUDA here: the root refuses, every rank hears about it
+    except RuntimeError as e:
+        assert "StreamWindow" in str(e)
+        open(os.path.join(out_dir, f"refused{rank}"), "w").write("1")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_stream_window_failure_is_collective(tmp_path):
+    """Peer memory needs GPUs; without them the set-up fails on EVERY rank with the root's reason instead of hanging."""
+    mp.spawn(_window_refused_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "refused0").exists() and (tmp_path / "refused1").exists()
