@@ -48,7 +48,7 @@ public:
     }
     int Decode(const uint8_t* in, int io, int il, uint8_t* out, int oo, int ol, bool known) override
     {
-        if (il == 0) return 0;
+        if (il == 0 || ol == 0) return 0;                                // LZ4Codec.cs:156-160, Safe.cs:470
         if (known) {
             if (lz4b200_uncompress((const char*)in + io, (char*)out + oo, il, ol) != il)      // Safe.cs:539-542
                 throw std::invalid_argument("LZ4 block is corrupted, or invalid length has been given.");
@@ -129,12 +129,15 @@ enum LZ4StreamFlags { None = 0, InteractiveRead = 1, HighCompression = 2, Isolat
 // difference is the dispatcher: up to `batchBlocks` buffered blocks go to the GPU in ONE batched call.
 class LZ4Stream {
 public:
-    LZ4Stream(std::ostream& inner, Context& ctx, int flags = Default, int blockSize = 1024 * 1024, int batchBlocks = 256)
+    // maxBufferBytes caps the write buffer and the read-ahead (whole blocks / chunks); with InteractiveRead the reader hands
+    // every chunk over as soon as it is read, like the reference (:376-401), instead of waiting for a batch of them.
+    LZ4Stream(std::ostream& inner, Context& ctx, int flags = Default, int blockSize = 1024 * 1024, int batchBlocks = 256,
+              size_t maxBufferBytes = 64u << 20)
         : out_(&inner), in_(nullptr), ctx_(ctx), hc_((flags & HighCompression) != 0), interactive_(false),
-          blockSize_(std::max(16, blockSize)), batch_(std::max(1, batchBlocks)) {}
-    LZ4Stream(std::istream& inner, Context& ctx, int flags = Default, int batchBlocks = 256)
+          blockSize_(std::max(16, blockSize)), batch_(std::max(1, batchBlocks)), maxBytes_(std::max<size_t>((size_t)blockSize_, maxBufferBytes)) {}
+    LZ4Stream(std::istream& inner, Context& ctx, int flags = Default, int batchBlocks = 256, size_t maxBufferBytes = 64u << 20)
         : out_(nullptr), in_(&inner), ctx_(ctx), hc_(false), interactive_((flags & InteractiveRead) != 0),
-          blockSize_(0), batch_(std::max(1, batchBlocks)) {}
+          blockSize_(0), batch_(std::max(1, batchBlocks)), maxBytes_(std::max<size_t>(1, maxBufferBytes)) {}
     ~LZ4Stream() { try { Close(); } catch (...) {} }
 
     bool CanRead() const { return in_ != nullptr; }
@@ -145,7 +148,7 @@ public:
     {
         if (!CanWrite()) throw std::runtime_error("Operation 'Write' is not supported");
         pending_.insert(pending_.end(), buffer + offset, buffer + offset + count);
-        const size_t full = (size_t)batch_ * (size_t)blockSize_;
+        const size_t full = std::min<size_t>((size_t)batch_, maxBytes_ / (size_t)blockSize_) * (size_t)blockSize_;
         // the reference flushes a full buffer only when MORE data arrives (:463-467); keep one byte back to do the same
         while (pending_.size() > full) emit(full);
     }
@@ -193,13 +196,16 @@ private:
     bool acquire()
     {
         raw_.clear(); ready_.clear(); rpos_ = 0;
-        for (int k = 0; k < batch_; k++) {
+        uint64_t decoded = 0;
+        for (int k = 0; k < (interactive_ ? 1 : batch_) && decoded < maxBytes_; k++) {
             uint64_t flags, rawLen, compLen;
             if (!read_varint(flags, true)) break;
             read_varint(rawLen, false);
             compLen = rawLen;
             if (flags & 1) read_varint(compLen, false);
-            if (compLen > rawLen) throw std::runtime_error("Unexpected end of stream");        // :288 corrupted
+            // :288 corrupted; both lengths are ints in the reference -- nothing larger is ever resized to
+            if (compLen > rawLen || rawLen > 0x7FFFFFFFull) throw std::runtime_error("Unexpected end of stream");
+            decoded += rawLen;
             const size_t at = raw_.size();
             raw_.resize(at + (size_t)compLen);
             in_->read((char*)raw_.data() + at, (std::streamsize)compLen);
@@ -219,6 +225,7 @@ private:
     std::ostream* out_; std::istream* in_; Context& ctx_;
     bool hc_, interactive_, closed_ = false;
     int blockSize_, batch_;
+    size_t maxBytes_;
     std::vector<uint8_t> pending_, raw_, ready_;
     size_t rpos_ = 0;
 };

@@ -266,7 +266,7 @@ class LZ4Codec:
             return bytes(out)
         inputLength = cls._check(input, inputOffset, inputLength, "input")
         outputLength = cls._check(output, outputOffset, outputLength, "output")
-        if inputLength == 0:
+        if inputLength == 0 or outputLength == 0:                    # CheckArguments :156-160 + `if (outputLength == 0) return 0` (Safe.cs:470)
             return 0
         return cls._service.Decode(input, inputOffset, inputLength, output, outputOffset, outputLength, knownOutputLength)
 
@@ -360,11 +360,13 @@ class LZ4Stream:
     """``LZ4Stream`` (src/LZ4/LZ4Stream.cs) over a Python binary file object.
 
     Wire format and chunk boundaries are the reference's (a chunk per ``blockSize`` bytes written, a partial chunk on
-    ``Flush``/``Close``, FlushCurrentChunk :239-269); the dispatcher differs: up to ``batchBlocks`` buffered blocks are
-    encoded / decoded by ONE batched GPU call instead of one block per call."""
+    ``Flush``/``Close``, FlushCurrentChunk :239-269); the dispatcher differs: up to ``batchBlocks`` buffered blocks (and at
+    most ``maxBufferBytes``) are encoded / decoded by ONE batched GPU call instead of one block per call.  With
+    ``InteractiveRead`` the reader decodes every chunk as soon as it has been read, like the reference (:376-401): a
+    socket or pipe that has delivered one chunk is never asked for the next one before the caller has seen the first."""
 
     def __init__(self, innerStream, compressionMode, compressionFlags=LZ4StreamFlags.Default, blockSize=1024 * 1024,
-                 batchBlocks=256, context: Optional[Context] = None):
+                 batchBlocks=256, context: Optional[Context] = None, maxBufferBytes=64 * 1024 * 1024):
         self._inner = innerStream
         self._mode = compressionMode
         self._hc = bool(compressionFlags & LZ4StreamFlags.HighCompression)
@@ -372,6 +374,7 @@ class LZ4Stream:
         self._isolate = bool(compressionFlags & LZ4StreamFlags.IsolateInnerStream)
         self._block = max(16, int(blockSize))                          # :131,138
         self._batch = max(1, int(batchBlocks))
+        self._max_bytes = max(self._block, int(maxBufferBytes))     # read-ahead / write buffer cap (whole blocks)
         self._ctx = context or default_context()
         self._pending = bytearray()
         self._ready = b""
@@ -394,7 +397,7 @@ class LZ4Stream:
             raise NotImplementedError("Operation 'Write' is not supported")
         count = len(buffer) - offset if count is None else count
         self._pending += bytes(buffer[offset:offset + count])
-        full = self._batch * self._block
+        full = min(self._batch, self._max_bytes // self._block) * self._block
         while len(self._pending) > full:          # a full buffer is flushed only when more data arrives (:463-467)
             self._emit(full)
 
@@ -439,14 +442,15 @@ class LZ4Stream:
 
     def _acquire(self):
         raw = bytearray()
-        for _ in range(self._batch):
+        decoded = 0
+        for _ in range(1 if self._interactive else self._batch):       # interactive: one chunk, then hand it over
             flags = self._read_varint(raw, True)
             if flags is None:
                 break
             raw_len = self._read_varint(raw, False)
             comp_len = self._read_varint(raw, False) if flags & 1 else raw_len
-            if comp_len > raw_len:
-                raise EOFError("Unexpected end of stream")             # :288 corrupted
+            if comp_len > raw_len or raw_len > 0x7FFFFFFF:
+                raise EOFError("Unexpected end of stream")             # :288 corrupted (lengths are ints in the reference)
             payload = self._inner.read(comp_len)
             while len(payload) < comp_len:                              # ReadBlock :205-221: no partial chunks
                 more = self._inner.read(comp_len - len(payload))
@@ -454,6 +458,9 @@ class LZ4Stream:
                     raise EOFError("Unexpected end of stream")
                 payload += more
             raw += payload
+            decoded += raw_len
+            if decoded >= self._max_bytes:                              # cap the read-ahead by bytes, not only by chunks
+                break
         if not raw:
             return False
         self._ready = self._ctx.stream_decode(bytes(raw))

@@ -414,6 +414,49 @@ def test_lz4stream_class_random_writes_and_reads(ctx, hc):
             LZ4Stream(io.BytesIO(wire[:-2]), LZ4StreamMode.Decompress, context=ctx).Read(len(data) + 1)
 
 
+def test_lz4stream_interactive_read_takes_one_chunk_at_a_time(ctx):
+    """InteractiveRead (src/LZ4/LZ4Stream.cs:376-401): a Read returns as soon as ONE chunk is decoded -- the inner stream
+    (a socket, a pipe) is not asked for the next chunk first.  The byte cap bounds the read-ahead and the write buffer of
+    the batching modes; Decode with an empty output returns 0 (LZ4Codec.Safe.cs:470)."""
+    import io
+    from lz4net_b200 import LZ4Codec, LZ4Stream, LZ4StreamFlags, LZ4StreamMode
+    bs = 4096
+    data = cases.content("ETEXT", 10 * bs, seed=9).tobytes()
+    wire = _ref_stream(data, bs, False)
+    ends, pos = [], 0                                                  # where each chunk of the wire ends
+    while pos < len(wire):
+        def varint(p):
+            v = sh = 0
+            while True:
+                b = wire[p]; p += 1; v |= (b & 0x7F) << sh; sh += 7
+                if not b & 0x80:
+                    return v, p
+        flags, pos = varint(pos); raw_len, pos = varint(pos)
+        comp_len, pos = varint(pos) if flags & 1 else (raw_len, pos)
+        pos += comp_len; ends.append(pos)
+    inner = io.BytesIO(wire)
+    r = LZ4Stream(inner, LZ4StreamMode.Decompress, LZ4StreamFlags.InteractiveRead, batchBlocks=256, context=ctx)
+    back = bytearray()
+    for k in range(len(ends)):
+        got = r.Read(1 << 20)
+        assert len(got) == bs and inner.tell() == ends[k]              # one chunk read, one chunk returned
+        back += got
+    assert r.Read(10) == b"" and bytes(back) == data
+    # the byte cap: 3 blocks of read-ahead per acquire although 256 chunks are allowed
+    inner = io.BytesIO(wire)
+    r = LZ4Stream(inner, LZ4StreamMode.Decompress, batchBlocks=256, context=ctx, maxBufferBytes=3 * bs)
+    assert len(r.Read(1)) == 1 and inner.tell() == ends[2]
+    assert r.Read(len(data)) == data[1:]
+    # ... and 2 blocks of write buffer: the third block's first byte pushes two chunks out
+    out = io.BytesIO()
+    w = LZ4Stream(out, LZ4StreamMode.Compress, LZ4StreamFlags.IsolateInnerStream, bs, batchBlocks=256, context=ctx, maxBufferBytes=2 * bs)
+    w.Write(data[:2 * bs]); assert out.tell() == 0
+    w.Write(data[2 * bs:2 * bs + 1]); assert out.tell() == ends[1]
+    w.Write(data[2 * bs + 1:]); w.Close()
+    assert out.getvalue() == wire
+    assert LZ4Codec.Decode(wire, 0, 10, bytearray(0), 0, 0, True) == 0
+
+
 @pytest.mark.parametrize("hc", [False, True])
 def test_encode_batch_packed(ctx, hc):
     """Packed host output: same per-block bytes and return values as the slot form, laid back to back in block order;
