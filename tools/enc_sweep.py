@@ -13,14 +13,13 @@ CLASSES = sys.argv[2].split(",") if len(sys.argv) > 2 else ("E0", "E50", "E100",
 CTAS = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else (0,)
 PF = [int(x) for x in sys.argv[4].split(",")] if len(sys.argv) > 4 else (1024,)
 VAR = [int(x) for x in sys.argv[5].split(",")] if len(sys.argv) > 5 else (2,)
-LW = [int(x) for x in sys.argv[6].split(",")] if len(sys.argv) > 6 else (1,)
 ctx = lz4net_b200.Context(0)
 peak = 6587.0
 for cls in CLASSES:
     w = Workload(ctx, nb, cls, nb, seed=2)
     rb = nb * BLOCK
     ref_len = None
-    for ctas, pf, var, lw in [(c, p, v, l) for l in LW for v in VAR for c in CTAS for p in PF]:
+    for ctas, pf, var in [(c, p, v) for v in VAR for c in CTAS for p in PF]:
         if True:
             ctx.set_option("encode_ctas_per_sm", ctas); ctx.set_option("encode_prefetch", pf); ctx.set_option("encode_variant", var)
             w.slots.zero_()
@@ -39,6 +38,6 @@ for cls in CLASSES:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(); w.encode(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1) * 1e-3)
             t = sorted(ts[1:])[1]
-            print(json.dumps({"cls": cls, "ratio": round(cs / rb, 4), "variant": var, "lane_warp": lw, "ctas": ctas, "prefetch": pf, "enc_gbs": round(rb / t / GB, 1),
+            print(json.dumps({"cls": cls, "ratio": round(cs / rb, 4), "variant": var, "ctas": ctas, "prefetch": pf, "enc_gbs": round(rb / t / GB, 1),
                               "enc_frac": round((rb + cs) / t / GB / peak, 4), "ms": round(t * 1e3, 2)}), flush=True)
     del w; torch.cuda.empty_cache()
