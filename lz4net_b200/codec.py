@@ -374,7 +374,8 @@ class LZ4Stream:
         self._isolate = bool(compressionFlags & LZ4StreamFlags.IsolateInnerStream)
         self._block = max(16, int(blockSize))                          # :131,138
         self._batch = max(1, int(batchBlocks))
-        self._max_bytes = max(self._block, int(maxBufferBytes))     # read-ahead / write buffer cap (whole blocks)
+        # write buffer cap (whole blocks, at least one) / read-ahead cap (whole chunks, at least one: blockSize is the WRITER's)
+        self._max_bytes = max(self._block if compressionMode == LZ4StreamMode.Compress else 1, int(maxBufferBytes))
         self._ctx = context or default_context()
         self._pending = bytearray()
         self._ready = b""
