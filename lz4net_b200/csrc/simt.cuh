@@ -44,7 +44,9 @@ SIMT_DEV uint4    ldg_v4(const void* p) { return *(const uint4*)p; }
 SIMT_DEV uint8_t  ldg_nc_u8(const uint8_t* p) { return __ldg(p); }
 SIMT_DEV uint32_t ldg_nc_u32(const void* p) { return __ldg((const uint32_t*)p); }
 SIMT_DEV uint4    ldg_nc_v4(const void* p) { return __ldg((const uint4*)p); }
+SIMT_DEV uint32_t ldg_u16(const uint16_t* p) { return *p; }
 SIMT_DEV void stg_u8(uint8_t* p, uint8_t v) { *p = v; }
+SIMT_DEV void stg_u16(uint16_t* p, uint32_t v) { *p = (uint16_t)v; }
 SIMT_DEV void stg_u32(void* p, uint32_t v) { *(uint32_t*)p = v; }
 SIMT_DEV void stg_v4(void* p, uint4 v) { *(uint4*)p = v; }
 // L2 residency hints (no extra instruction: the policy travels in the access descriptor).  keep = evict-last, for input
@@ -70,6 +72,9 @@ SIMT_DEV uint4 lds_v4(smem_ref r, uint32_t off) { uint4 v; asm volatile("ld.shar
 SIMT_DEV void sts_u8(smem_ref r, uint32_t off, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(r.a + off), "r"(v) : "memory"); }
 SIMT_DEV void sts_u16(smem_ref r, uint32_t off, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" :: "r"(r.a + off), "h"((uint16_t)v) : "memory"); }
 SIMT_DEV void sts_u32(smem_ref r, uint32_t off, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(r.a + off), "r"(v) : "memory"); }
+SIMT_DEV void sts_v4(smem_ref r, uint32_t off, uint4 v) { asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(r.a + off), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); }
+// shared-memory atomic add on an aligned 32-bit word, returns the old word (ATOMS.ADD)
+SIMT_DEV uint32_t atoms_add(smem_ref r, uint32_t off, uint32_t v) { uint32_t o; asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(o) : "r"(r.a + off), "r"(v) : "memory"); return o; }
 
 // Ampere-style asynchronous copy, 16 bytes global -> shared per lane (both addresses 16-byte aligned), tracked per thread:
 // every lane of a warp copies for itself in ONE instruction (the bulk form, UBLKCP, takes uniform operands and would be

@@ -108,6 +108,26 @@ def encode_hc(block, cap=None, src_skew=0):
     return int(r), d[32:32 + max(r, 0)].tobytes()
 
 
+HCW_FALLBACK = -2 ** 31
+
+
+def encode_hcw(block, cap=None, src_skew=0, dst_skew=0, sched_seed=1):
+    """The warp-per-block HC encoder (lz4hc_warp.cuh).  Returns (result, bytes); result == HCW_FALLBACK when the kernel hands
+    the block to the thread-per-block one."""
+    n = len(block)
+    if cap is None:
+        cap = n + n // 255 + 16
+    a = np.zeros(src_skew + n + 64, np.uint8)
+    a[src_skew:src_skew + n] = np.frombuffer(block, np.uint8)
+    lo = 32 + dst_skew
+    d = np.full(max(cap, 0) + 96 + dst_skew, 0xCD, np.uint8)
+    f = lib().emu_encode_hcw
+    f.restype = C.c_int
+    r = f(C.c_void_p(a.ctypes.data + src_skew), n, C.c_void_p(d.ctypes.data + lo), cap, C.c_uint64(sched_seed))
+    assert (d[:lo] == 0xCD).all() and (d[lo + max(cap, 0):] == 0xCD).all(), "HC warp encoder wrote outside [dst, dst+cap)"
+    return int(r), d[lo:lo + max(r, 0)].tobytes()
+
+
 def encode_guarded(block, sched_seed=1, variant=2, end_pad=0):
     """Encode one block whose last byte is the last byte of a readable page: the page after it is PROT_NONE, so any
     read of a word that holds no input byte (an over-read past the end of the input) kills the process with SIGSEGV.

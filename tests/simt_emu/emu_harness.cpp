@@ -6,6 +6,7 @@
 #include "lz4_decode_lpb.cuh"
 #include "lz4_encode.cuh"
 #include "lz4hc_encode.cuh"
+#include "lz4hc_warp.cuh"
 #include <stdlib.h>
 #include <vector>
 
@@ -130,6 +131,23 @@ int emu_encode_hc(const uint8_t* src, int n, uint8_t* dst, int cap)
     int r = hc_encode_block(st, src, n, dst, cap);
     free(st);
     return r;
+}
+
+// the warp-per-block HC encoder (static index); returns HCW_FALLBACK when the block is handed to the scalar kernel
+struct HcwJob { const uint8_t* src; int n; uint8_t* dst; int cap; int result; void* sm; void* index; };
+static void hcw_entry(int lane, void* arg)
+{
+    HcwJob* j = (HcwJob*)arg;
+    const int r = hcw_encode_block(simt::smem_ref_of(j->sm), j->index, j->src, j->n, j->dst, j->cap, lane);
+    if (lane == 0) j->result = r;
+}
+int emu_encode_hcw(const uint8_t* src, int n, uint8_t* dst, int cap, uint64_t sched_seed)
+{
+    HcwJob j{src, n, dst, cap, 0, aligned_alloc(16, HCW_SMEM_BYTES), aligned_alloc(16, HCW_INDEX_BYTES)};
+    memset(j.sm, 0x5A, HCW_SMEM_BYTES); memset(j.index, 0xA5, HCW_INDEX_BYTES);     // stale garbage, like a reused slot
+    simt_emu::run_warp(hcw_entry, &j, sched_seed);
+    free(j.sm); free(j.index);
+    return j.result;
 }
 
 void emu_set_encode_variant(int v) { g_enc_variant = v; }

@@ -44,6 +44,8 @@ static inline uint4    ldg_v4(const void* p) { uint4 v; memcpy(&v, p, 16); retur
 static inline uint8_t  ldg_nc_u8(const uint8_t* p) { return *p; }
 static inline uint32_t ldg_nc_u32(const void* p) { return ldg_u32(p); }
 static inline uint4    ldg_nc_v4(const void* p) { return ldg_v4(p); }
+static inline uint32_t ldg_u16(const uint16_t* p) { return *p; }
+static inline void stg_u16(uint16_t* p, uint32_t v) { *p = (uint16_t)v; }
 static inline void stg_u8(uint8_t* p, uint8_t v) { *p = v; }
 static inline void stg_u32(void* p, uint32_t v) { memcpy(p, &v, 4); }
 static inline void stg_v4(void* p, uint4 v) { memcpy(p, &v, 16); }
@@ -61,6 +63,10 @@ static inline uint4 lds_v4(smem_ref r, uint32_t off) { uint4 v; memcpy(&v, r.p +
 static inline void sts_u8(smem_ref r, uint32_t off, uint32_t v) { r.p[off] = (uint8_t)v; }
 static inline void sts_u16(smem_ref r, uint32_t off, uint32_t v) { uint16_t t = (uint16_t)v; memcpy(r.p + off, &t, 2); }
 static inline void sts_u32(smem_ref r, uint32_t off, uint32_t v) { memcpy(r.p + off, &v, 4); }
+static inline void sts_v4(smem_ref r, uint32_t off, uint4 v) { memcpy(r.p + off, &v, 16); }
+// a lane is only descheduled inside a collective, so a plain read-modify-write is atomic here; lanes reach it in the
+// scheduler's pseudo-random order, like the hardware's unspecified order among the lanes of one ATOMS
+static inline uint32_t atoms_add(smem_ref r, uint32_t off, uint32_t v) { uint32_t o; memcpy(&o, r.p + off, 4); uint32_t n = o + v; memcpy(r.p + off, &n, 4); return o; }
 // cp.async: the copy is DEFERRED until the wait that covers its group (per lane), so that code which reads a unit before
 // waiting for it, or overwrites a ring slot that is still to be read, fails in the emulator as well
 void cp_async16_emu(void* sdst, const void* gsrc);
