@@ -2,6 +2,7 @@
 #include "kernels.h"
 #include "lz4_encode.cuh"
 #include "lz4hc_encode.cuh"
+#include "lz4hc_warp.cuh"
 
 namespace lz4b200 {
 
@@ -100,6 +101,80 @@ cudaError_t launch_encode_hc(const BatchArgs& a, void* scratch, int concurrency,
     if (ctas > want) ctas = want;
     if (ctas < 1) ctas = 1;
     lz4_encode_hc_kernel<<<(unsigned)ctas, HC_THREADS, 0, stream>>>(a, (uint8_t*)scratch, counter);
+    if (launches) ++*launches;
+    return cudaGetLastError();
+}
+
+// ---- HC encoder, blocks <= 64 KiB: one WARP per block on a static index (lz4hc_warp.cuh) -----------------------------
+// One 32-thread CTA per warp: the block's bytes take 64 KiB of shared memory, so at most three CTAs share an SM; fewer are
+// forced by asking for more shared memory than the CTA uses.  Each CTA owns HCW_INDEX_BYTES of the scratch arena (its
+// rank / sorted tables, L2-resident: 148 x 3 x 256 KiB = 111 MB).
+__global__ void __launch_bounds__(32)
+lz4_encode_hcw_kernel(BatchArgs a, uint8_t* arena, uint32_t* counter)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const simt::smem_ref sm = simt::smem_ref_of(smem);
+    void* index = arena + (size_t)blockIdx.x * HCW_INDEX_BYTES;
+    const int lane = threadIdx.x;
+    for (;;) {
+        uint32_t b = 0;
+        if (lane == 0) b = atomicAdd(counter, 1u);
+        b = simt::shfl(0xFFFFFFFFu, b, 0);
+        if (b >= (uint32_t)a.n_blocks) break;
+        const int r = hcw_encode_block(sm, index, a.src + a.src_off[b], a.src_len[b], a.dst + a.dst_off[b], a.dst_cap[b], lane);
+        if (lane == 0) a.out_len[b] = r;
+        simt::syncwarp(0xFFFFFFFFu);                       // the next block reuses the shared memory and the index
+    }
+}
+
+// the blocks the warp kernel handed back (larger than 64 KiB, or a state its static index does not describe): exact
+// thread-per-block encoder, each thread looks at a stride of the batch
+__global__ void __launch_bounds__(HC_THREADS)
+lz4_encode_hc_marked_kernel(BatchArgs a, uint8_t* arena)
+{
+    const size_t slot = (size_t)blockIdx.x * HC_THREADS + threadIdx.x;
+    void* state = arena + slot * HC_STATE_BYTES;
+    const size_t stride = (size_t)gridDim.x * HC_THREADS;
+    for (size_t b = slot; b < (size_t)a.n_blocks; b += stride)
+        if (a.out_len[b] == HCW_FALLBACK)
+            a.out_len[b] = hc_encode_block(state, a.src + a.src_off[b], a.src_len[b], a.dst + a.dst_off[b], a.dst_cap[b]);
+}
+
+constexpr int HCW_FALLBACK_THREADS = 4096;                 // thread-per-block slots kept for handed-back blocks (1 GiB of state)
+
+static int hcw_grid(int32_t n_blocks, int warps_per_sm, const DeviceInfo& dev)
+{
+    if (warps_per_sm < 1 || warps_per_sm > 3) warps_per_sm = 3;
+    long long g = (long long)dev.num_sms * warps_per_sm;
+    if (g > n_blocks) g = n_blocks;
+    return g < 1 ? 1 : (int)g;
+}
+
+size_t hcw_scratch_bytes(int32_t n_blocks, int warps_per_sm, const DeviceInfo& dev)
+{
+    const size_t index = (size_t)hcw_grid(n_blocks, warps_per_sm, dev) * HCW_INDEX_BYTES;
+    const size_t back = hc_scratch_bytes((int)(n_blocks < HCW_FALLBACK_THREADS ? (n_blocks < 1 ? 1 : n_blocks) : HCW_FALLBACK_THREADS));
+    return index > back ? index : back;                    // the two kernels run one after the other on the same arena
+}
+
+cudaError_t launch_encode_hcw(const BatchArgs& a, void* scratch, int warps_per_sm, uint32_t* counter,
+                              const DeviceInfo& dev, cudaStream_t stream, int64_t* launches)
+{
+    if (a.n_blocks <= 0) return cudaSuccess;
+    if (warps_per_sm < 1 || warps_per_sm > 3) warps_per_sm = 3;
+    // residency: the CTA needs HCW_SMEM_BYTES; asking for a larger share of the SM keeps the others out
+    int dyn = HCW_SMEM_BYTES;
+    if (warps_per_sm < 3) { const int share = dev.smem_per_sm / warps_per_sm - 2048; if (share > dyn) dyn = share < dev.smem_optin ? share : dev.smem_optin; }
+    cudaError_t e = cudaFuncSetAttribute(lz4_encode_hcw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), stream);
+    if (e != cudaSuccess) return e;
+    lz4_encode_hcw_kernel<<<(unsigned)hcw_grid(a.n_blocks, warps_per_sm, dev), 32, dyn, stream>>>(a, (uint8_t*)scratch, counter);
+    if (launches) ++*launches;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const int back = a.n_blocks < HCW_FALLBACK_THREADS ? a.n_blocks : HCW_FALLBACK_THREADS;
+    lz4_encode_hc_marked_kernel<<<(unsigned)((back + HC_THREADS - 1) / HC_THREADS), HC_THREADS, 0, stream>>>(a, (uint8_t*)scratch);
     if (launches) ++*launches;
     return cudaGetLastError();
 }

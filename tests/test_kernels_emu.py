@@ -267,3 +267,94 @@ def test_encode_hc_above_64k():
     for m, n in (("ETEXT", 70001), ("periodic", 140000), ("E100", 200000), ("mixed", 131072)):
         d = cases.content(m, n, seed=9).tobytes()
         assert emu.encode_hc(d) == oracle.encode_hc(d), (m, n)
+
+
+# ---- LZ4HC, one WARP per block on a static index (lz4hc_warp.cuh) -----------------------------------------------------
+def _hcw_check(d, cap=None, **kw):
+    """The warp kernel either emits the reference's bytes or hands the block back (never anything else)."""
+    r, o = emu.encode_hcw(d, cap=cap, **kw)
+    if r == emu.HCW_FALLBACK:
+        return False
+    assert (r, o) == oracle.encode_hc(d, cap=cap), (len(d), cap, kw)
+    return True
+
+
+@pytest.mark.parametrize("model", cases.MODELS)
+def test_encode_hcw_matches_oracle(model):
+    """Byte-identical to LZ4_compressHC_limitedOutput (original/lz4hc.c:745-755): the chain walks of :423-433 / :477-514
+    replaced by gathers from the sorted hash buckets."""
+    done = 0
+    for i, n in enumerate([65536, 65535, 4097] + cases.random_lengths(4, 65536, seed=5)):
+        d = cases.content(model, n, seed=500 + i).tobytes()
+        done += _hcw_check(d, sched_seed=3 + i)
+    assert done >= 6, "the static index should describe (nearly) every block"
+
+
+def test_encode_hcw_boundary_lengths():
+    for n in cases.BOUNDARY_LENGTHS:
+        if n <= 65536:
+            for m in ("lowent", "periodic", "E50", "E100"):
+                assert _hcw_check(cases.content(m, n, seed=n).tobytes(), sched_seed=n + 1), (m, n)
+
+
+def test_encode_hcw_limited_output_and_alignment():
+    for i, m in enumerate(("ETEXT", "lowent", "E50", "periodic", "runs", "E0")):
+        d = cases.content(m, 5000, seed=40 + i).tobytes()
+        r, _ = oracle.encode_hc(d)
+        for cap in (r, r - 1, len(d), len(d) - 1, r // 2, 0, 1, 7, 8, 13):
+            assert _hcw_check(d, cap=cap), (m, cap)
+        for skew in range(1, 16):
+            assert _hcw_check(d, src_skew=skew, dst_skew=(skew * 5) % 16, sched_seed=skew), (m, skew)
+    # the capacity swept over a whole compressed block: every limit check of :529 / :541 / :731 fails once
+    d = cases.content("ETEXT", 1200, seed=5).tobytes()
+    r, _ = oracle.encode_hc(d)
+    for cap in range(0, r + 3):
+        assert _hcw_check(d, cap=cap), cap
+
+
+def test_encode_hcw_fuzz():
+    """Random models / lengths / capacities / alignments / lane schedules."""
+    rng = np.random.default_rng(20260924)
+    handed_back = 0
+    for trial in range(60):
+        m = cases.MODELS[int(rng.integers(len(cases.MODELS)))]
+        n = int(np.exp(rng.random() * np.log(65536)))
+        d = cases.content(m, n, seed=int(rng.integers(1 << 30))).tobytes()
+        cap = None
+        if rng.integers(3) == 0:
+            cap = int(rng.integers(0, oracle.encode_hc(d)[0] + 4))
+        handed_back += not _hcw_check(d, cap=cap, src_skew=int(rng.integers(16)), dst_skew=int(rng.integers(16)),
+                                      sched_seed=int(rng.integers(1, 1 << 20)))
+    assert handed_back <= 2
+
+
+def test_encode_hcw_upstream_fuzzer_buffers():
+    for seed in range(6):
+        from lz4net_b200 import synth
+        d = synth.fuz_block(seed, 20000).tobytes()
+        assert _hcw_check(d, sched_seed=seed + 1), seed
+
+
+def _hash15(b4):
+    return ((int.from_bytes(b4, "little") * 2654435761) & 0xFFFFFFFF) >> 17
+
+
+def test_encode_hcw_hands_back_what_the_static_index_does_not_describe():
+    """Larger than 64 KiB; and a run of period 3 two of whose strings share a hash bucket: the reference's repeat detector
+    (original/lz4hc.c:437-455) writes chain deltas of 3 across positions whose real predecessor in the bucket is 1 back."""
+    assert emu.encode_hcw(cases.content("ETEXT", 65537, seed=1).tobytes())[0] == emu.HCW_FALLBACK
+    found = None
+    for a in range(1, 256):
+        for b in range(a + 1, 256):
+            for c in range(b + 1, 256):
+                s0, s1, s2 = bytes([a, b, c, a]), bytes([b, c, a, b]), bytes([c, a, b, c])
+                if _hash15(s1) == _hash15(s2) and _hash15(s0) != _hash15(s1):
+                    found = (a, b, c); break
+            if found: break
+        if found: break
+    assert found, "no colliding triple"
+    rng = np.random.default_rng(3)
+    d = rng.integers(0, 256, 500, dtype=np.uint8).tobytes() + bytes(found) * 200 + rng.integers(0, 256, 500, dtype=np.uint8).tobytes()
+    assert emu.encode_hcw(d)[0] == emu.HCW_FALLBACK
+    # the same run with a triple that does not collide is encoded here
+    assert _hcw_check(rng.integers(0, 256, 500, dtype=np.uint8).tobytes() + bytes([1, 2, 3]) * 200 + bytes(500))
