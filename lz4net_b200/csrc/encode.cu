@@ -105,11 +105,14 @@ cudaError_t launch_encode_hc(const BatchArgs& a, void* scratch, int concurrency,
     return cudaGetLastError();
 }
 
+constexpr int HCW_GLOBAL_MAX_WARPS = 32;                   // global variant: CTAs per SM the register budget is cut for
+
 // ---- HC encoder, blocks <= 64 KiB: one WARP per block on a static index (lz4hc_warp.cuh) -----------------------------
-// One 32-thread CTA per warp: the block's bytes take 64 KiB of shared memory, so at most three CTAs share an SM; fewer are
-// forced by asking for more shared memory than the CTA uses.  Each CTA owns HCW_INDEX_BYTES of the scratch arena (its
-// rank / sorted tables, L2-resident: 148 x 3 x 256 KiB = 111 MB).
-__global__ void __launch_bounds__(32)
+// One 32-thread CTA per warp.  SMEM variant: the block's bytes take 64 KiB of shared memory, so at most three CTAs share an
+// SM (fewer are forced by asking for more shared memory than the CTA uses).  Global variant: no shared memory, up to 32
+// CTAs per SM, the block read through L1 / L2.  Each CTA owns HCW_INDEX_BYTES of the scratch arena (rank / sorted tables).
+template <bool SMEM>
+__global__ void __launch_bounds__(32, SMEM ? 3 : HCW_GLOBAL_MAX_WARPS)
 lz4_encode_hcw_kernel(BatchArgs a, uint8_t* arena, uint32_t* counter)
 {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -121,7 +124,7 @@ lz4_encode_hcw_kernel(BatchArgs a, uint8_t* arena, uint32_t* counter)
         if (lane == 0) b = atomicAdd(counter, 1u);
         b = simt::shfl(0xFFFFFFFFu, b, 0);
         if (b >= (uint32_t)a.n_blocks) break;
-        const int r = hcw_encode_block(sm, index, a.src + a.src_off[b], a.src_len[b], a.dst + a.dst_off[b], a.dst_cap[b], lane);
+        const int r = hcw_encode_block<SMEM>(sm, index, a.src + a.src_off[b], a.src_len[b], a.dst + a.dst_off[b], a.dst_cap[b], lane);
         if (lane == 0) a.out_len[b] = r;
         simt::syncwarp(0xFFFFFFFFu);                       // the next block reuses the shared memory and the index
     }
@@ -142,34 +145,46 @@ lz4_encode_hc_marked_kernel(BatchArgs a, uint8_t* arena)
 
 constexpr int HCW_FALLBACK_THREADS = 4096;                 // thread-per-block slots kept for handed-back blocks (1 GiB of state)
 
-static int hcw_grid(int32_t n_blocks, int warps_per_sm, const DeviceInfo& dev)
+static int hcw_warps(int variant, int warps_per_sm) { const int mx = variant == 1 ? 3 : 32; return warps_per_sm < 1 || warps_per_sm > mx ? (variant == 1 ? 3 : 16) : warps_per_sm; }
+
+static int hcw_grid(int32_t n_blocks, int variant, int warps_per_sm, const DeviceInfo& dev)
 {
-    if (warps_per_sm < 1 || warps_per_sm > 3) warps_per_sm = 3;
-    long long g = (long long)dev.num_sms * warps_per_sm;
+    long long g = (long long)dev.num_sms * hcw_warps(variant, warps_per_sm);
     if (g > n_blocks) g = n_blocks;
     return g < 1 ? 1 : (int)g;
 }
 
-size_t hcw_scratch_bytes(int32_t n_blocks, int warps_per_sm, const DeviceInfo& dev)
+size_t hcw_scratch_bytes(int32_t n_blocks, int variant, int warps_per_sm, const DeviceInfo& dev)
 {
-    const size_t index = (size_t)hcw_grid(n_blocks, warps_per_sm, dev) * HCW_INDEX_BYTES;
+    const size_t index = (size_t)hcw_grid(n_blocks, variant, warps_per_sm, dev) * HCW_INDEX_BYTES;
     const size_t back = hc_scratch_bytes((int)(n_blocks < HCW_FALLBACK_THREADS ? (n_blocks < 1 ? 1 : n_blocks) : HCW_FALLBACK_THREADS));
     return index > back ? index : back;                    // the two kernels run one after the other on the same arena
 }
 
-cudaError_t launch_encode_hcw(const BatchArgs& a, void* scratch, int warps_per_sm, uint32_t* counter,
+// variant 1: block staged in shared memory (<= 3 warps per SM); 2: nothing in shared memory (<= 32 warps per SM)
+cudaError_t launch_encode_hcw(const BatchArgs& a, void* scratch, int variant, int warps_per_sm, uint32_t* counter,
                               const DeviceInfo& dev, cudaStream_t stream, int64_t* launches)
 {
     if (a.n_blocks <= 0) return cudaSuccess;
-    if (warps_per_sm < 1 || warps_per_sm > 3) warps_per_sm = 3;
-    // residency: the CTA needs HCW_SMEM_BYTES; asking for a larger share of the SM keeps the others out
-    int dyn = HCW_SMEM_BYTES;
-    if (warps_per_sm < 3) { const int share = dev.smem_per_sm / warps_per_sm - 2048; if (share > dyn) dyn = share < dev.smem_optin ? share : dev.smem_optin; }
-    cudaError_t e = cudaFuncSetAttribute(lz4_encode_hcw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+    const int warps = hcw_warps(variant, warps_per_sm);
+    const int grid = hcw_grid(a.n_blocks, variant, warps_per_sm, dev);
+    cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), stream);
     if (e != cudaSuccess) return e;
-    e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), stream);
-    if (e != cudaSuccess) return e;
-    lz4_encode_hcw_kernel<<<(unsigned)hcw_grid(a.n_blocks, warps_per_sm, dev), 32, dyn, stream>>>(a, (uint8_t*)scratch, counter);
+    if (variant == 1) {
+        // residency: the CTA needs HCW_SMEM_BYTES; asking for a larger share of the SM keeps the others out
+        int dyn = HCW_SMEM_BYTES;
+        if (warps < 3) { const int share = dev.smem_per_sm / warps - 2048; if (share > dyn) dyn = share < dev.smem_optin ? share : dev.smem_optin; }
+        e = cudaFuncSetAttribute(lz4_encode_hcw_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+        if (e != cudaSuccess) return e;
+        lz4_encode_hcw_kernel<true><<<(unsigned)grid, 32, dyn, stream>>>(a, (uint8_t*)scratch, counter);
+    } else {
+        // all of the SM's on-chip memory as L1 (the blocks' bytes are re-read at random).  Residency below 32 CTAs per SM
+        // is a matter of the grid alone: CTAs are placed breadth-first over the SMs and the kernel is persistent.
+        e = cudaFuncSetAttribute(lz4_encode_hcw_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+        if (e != cudaSuccess) return e;
+        const int dyn = 0;
+        lz4_encode_hcw_kernel<false><<<(unsigned)grid, 32, dyn, stream>>>(a, (uint8_t*)scratch, counter);
+    }
     if (launches) ++*launches;
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;

@@ -26,8 +26,9 @@ size_t      hc_scratch_bytes(int concurrency);
 cudaError_t launch_encode_hc(const BatchArgs& a, void* scratch, int concurrency, uint32_t* counter,
                              const DeviceInfo& dev, cudaStream_t stream, int64_t* launches);
 // blocks <= 64 KiB: one warp per block on a static index, followed by the thread-per-block kernel over the blocks it handed back
-size_t      hcw_scratch_bytes(int32_t n_blocks, int warps_per_sm, const DeviceInfo& dev);
-cudaError_t launch_encode_hcw(const BatchArgs& a, void* scratch, int warps_per_sm, uint32_t* counter,
+// (variant 1: the block staged in shared memory, <= 3 warps per SM; 2: nothing in shared memory, <= 32 warps per SM)
+size_t      hcw_scratch_bytes(int32_t n_blocks, int variant, int warps_per_sm, const DeviceInfo& dev);
+cudaError_t launch_encode_hcw(const BatchArgs& a, void* scratch, int variant, int warps_per_sm, uint32_t* counter,
                               const DeviceInfo& dev, cudaStream_t stream, int64_t* launches);
 cudaError_t launch_compact(const uint8_t* slots, const int64_t* slot_off, const int32_t* len, uint8_t* packed,
                            int64_t* out_off, int32_t n_blocks, void* scan_tmp, size_t scan_tmp_bytes,

@@ -34,38 +34,69 @@
 namespace lz4b200 {
 
 constexpr int    HCW_MAX_BLOCK   = 65536;
-constexpr size_t HCW_INDEX_BYTES = 2u * 65536u * sizeof(uint16_t);    // rank[65536] + sorted[65536] per warp in flight
-constexpr int    HCW_SMEM_BYTES  = 65536 + 16;                        // bucket counters during the build, then the block's bytes
+// per warp in flight: rank[65536] + sorted[65536] (u16) + the build's bucket counters (u16[32768]; only used by the
+// variant that keeps nothing in shared memory)
+constexpr size_t HCW_INDEX_BYTES = 2u * 65536u * sizeof(uint16_t) + 32768u * sizeof(uint16_t);
+constexpr int    HCW_SMEM_BYTES  = 65536 + 16;                        // SMEM variant: bucket counters during the build, then the block's bytes
 constexpr int    HCW_FALLBACK    = (int)0x80000000;                   // out_len marker: this block needs the scalar kernel
 constexpr uint32_t HCW_FULL      = 0xFFFFFFFFu;
 
+// Two placements of the block's bytes and of the build's counters, same code otherwise:
+//   SMEM = true : both in 64 KiB of shared memory (counters first, then the staged block): candidate bytes at LDS latency,
+//                 three warps (blocks) per SM;
+//   SMEM = false: the block is read through the read-only path (L1 / L2), the counters live in the warp's arena slot
+//                 (global atomics): no shared memory, as many warps per SM as the launch asks for.
+template <bool SMEM>
 struct Hcw {
-    simt::smem_ref sm;            // HCW_SMEM_BYTES
+    simt::smem_ref sm;            // SMEM: HCW_SMEM_BYTES
+    uint32_t* cnt;                // !SMEM: 16384 words of packed u16 counters
+    InWords in;                   // the input through aligned 32-bit words (the build; !SMEM: every read)
     uint16_t* rank;               // rank[p]: index of position p in `sorted` (positions 1 .. mflimit-1)
     uint16_t* sorted;             // positions ordered by (hash, position)
     const uint8_t* src; int n, lane, mflimit, matchlimit;
     uint32_t v0;                  // the four bytes at position 0 (the end of every walk)
+
+    // four bytes / one byte at position p of the block (p + 3 < n)
+    SIMT_MEM uint32_t rd32(uint32_t p) const
+    {
+        if (SMEM) { const uint32_t q = p & ~3u; return simt::funnel_r(simt::lds_u32(sm, q), simt::lds_u32(sm, q + 4), (p & 3u) * 8u); }
+        return in.at((int)p);
+    }
+    SIMT_MEM uint32_t rd8(uint32_t p) const { return SMEM ? simt::lds_u8(sm, p) : (uint32_t)simt::ldg_nc_u8(src + p); }
+    // the build's counters: u16, two to a word, word w at byte 4w
+    SIMT_MEM void cnt_zero() const
+    {
+        if (SMEM) for (uint32_t i = (uint32_t)lane * 16u; i < 65536u; i += 512u) simt::sts_v4(sm, i, uint4{0, 0, 0, 0});
+        else      for (uint32_t i = (uint32_t)lane * 4u; i < 16384u; i += 128u) simt::stg_v4(cnt + i, uint4{0, 0, 0, 0});
+    }
+    SIMT_MEM uint32_t cnt_add(uint32_t h) const                      // bucket h's counter += 1, returns the old counter
+    {
+        const uint32_t inc = (h & 1u) ? 0x10000u : 1u;
+        const uint32_t o = SMEM ? simt::atoms_add(sm, (h >> 1) * 4u, inc) : simt::atomg_add(cnt + (h >> 1), inc);
+        return (o >> ((h & 1u) * 16u)) & 0xFFFFu;
+    }
+    SIMT_MEM uint32_t cnt_get(uint32_t h) const
+    {
+        if (SMEM) return simt::lds_u16(sm, h * 2u);
+        return (simt::ldg_u32(cnt + (h >> 1)) >> ((h & 1u) * 16u)) & 0xFFFFu;
+    }
+    SIMT_MEM uint32_t cnt_word(uint32_t wi) const { return SMEM ? simt::lds_u32(sm, wi * 4u) : simt::ldg_u32(cnt + wi); }
+    SIMT_MEM void cnt_word_set(uint32_t wi, uint32_t v) const { if (SMEM) simt::sts_u32(sm, wi * 4u, v); else simt::stg_u32(cnt + wi, v); }
 };
 
 SIMT_DEV uint32_t hcw_hash(uint32_t v) { return (v * 2654435761u) >> 17; }                   // :245-246 HASH_LOG 15
 
-// four bytes at position p of the block staged in shared memory (two aligned words, SHF)
-SIMT_DEV uint32_t hcw_sm32(const Hcw& w, uint32_t p)
-{
-    const uint32_t q = p & ~3u;
-    return simt::funnel_r(simt::lds_u32(w.sm, q), simt::lds_u32(w.sm, q + 4), (p & 3u) * 8u);
-}
-
 // equal bytes of [a..) and [b..), a < limit  (== the 8/4/2/1 scheme of :376-391); one lane
-SIMT_DEV int hcw_common(const Hcw& w, int a, int b, int limit)
+template <bool SMEM>
+SIMT_DEV int hcw_common(const Hcw<SMEM>& w, int a, int b, int limit)
 {
     const int a0 = a;
     while (a + 4 <= limit) {
-        const uint32_t x = hcw_sm32(w, (uint32_t)a) ^ hcw_sm32(w, (uint32_t)b);
+        const uint32_t x = w.rd32((uint32_t)a) ^ w.rd32((uint32_t)b);
         if (x) return a - a0 + ((simt::ffs(x) - 1) >> 3);
         a += 4; b += 4;
     }
-    while (a < limit && simt::lds_u8(w.sm, (uint32_t)a) == simt::lds_u8(w.sm, (uint32_t)b)) { a++; b++; }
+    while (a < limit && w.rd8((uint32_t)a) == w.rd8((uint32_t)b)) { a++; b++; }
     return a - a0;
 }
 
@@ -78,28 +109,38 @@ struct HcwSmemSrc {
     SIMT_MEM uint4 word(uint32_t i, int k) const { return simt::lds_v4(sm, ((at + i) & ~15u) + 16u * (uint32_t)k); }
 };
 
+// the same through the read-only path (not pipelined: the warp's registers are worth more as resident warps here)
+struct HcwInputSrc {
+    static constexpr bool PIPELINED = false;
+    const uint8_t* p;
+    SIMT_MEM uint8_t byte(uint32_t i) const { return simt::ldg_nc_u8(p + i); }
+    SIMT_MEM uint32_t misalign(uint32_t i) const { return (uint32_t)((uintptr_t)(p + i) & 15); }
+    SIMT_MEM uint4 word(uint32_t i, int k) const { return simt::ldg_nc_v4((const uint8_t*)(((uintptr_t)(p + i)) & ~(uintptr_t)15) + 16 * k); }
+};
+
 // ---- 1. the index ---------------------------------------------------------------------------------------------------
-SIMT_DEV void hcw_build(const Hcw& w)
+template <bool SMEM>
+SIMT_DEV void hcw_build(const Hcw<SMEM>& w)
 {
     const int lane = w.lane, P = w.mflimit;                               // positions 1 .. P-1 are ever searched or walked to
-    for (uint32_t i = (uint32_t)lane * 16u; i < 65536u; i += 512u) simt::sts_v4(w.sm, i, uint4{0, 0, 0, 0});
+    const InWords& in = w.in;
+    w.cnt_zero();
     simt::syncwarp(HCW_FULL);
-    InWords in; in.init(w.src);
-    // bucket sizes: u16 counters, two to a word, ATOMS on the word (a bucket never holds 65536 positions: no carry)
+    // bucket sizes: u16 counters, two to a word, atomic adds on the word (a bucket never holds 65536 positions: no carry)
     for (int base = 1; base < P; base += 32) {
         const int p = base + lane;
-        if (p < P) { const uint32_t h = hcw_hash(in.at(p)); simt::atoms_add(w.sm, (h >> 1) * 4u, (h & 1u) ? 0x10000u : 1u); }
+        if (p < P) w.cnt_add(hcw_hash(in.at(p)));
     }
     simt::syncwarp(HCW_FULL);
     // exclusive prefix sum in place: counter -> first index of the bucket
     uint32_t carry = 0;
     for (uint32_t w0 = 0; w0 < 16384u; w0 += 32u) {
-        const uint32_t v = simt::lds_u32(w.sm, (w0 + lane) * 4u), lo = v & 0xFFFFu, hi = v >> 16, s = lo + hi;
+        const uint32_t v = w.cnt_word(w0 + lane), lo = v & 0xFFFFu, hi = v >> 16, s = lo + hi;
         uint32_t x = s;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { const uint32_t y = simt::shfl(HCW_FULL, x, lane >= d ? lane - d : lane); if (lane >= d) x += y; }
         const uint32_t excl = x - s + carry;
-        simt::sts_u32(w.sm, (w0 + lane) * 4u, (excl & 0xFFFFu) | ((excl + lo) << 16));
+        w.cnt_word_set(w0 + lane, (excl & 0xFFFFu) | ((excl + lo) << 16));
         carry += simt::shfl(HCW_FULL, x, 31);
     }
     simt::syncwarp(HCW_FULL);
@@ -110,10 +151,10 @@ SIMT_DEV void hcw_build(const Hcw& w)
         const int p = base + lane;
         const bool act = p < P;
         const uint32_t h = act ? hcw_hash(in.at(p)) : 0xFFFFFFFFu;
-        const uint32_t c0 = act ? simt::lds_u16(w.sm, h * 2u) : 0u;
+        const uint32_t c0 = act ? w.cnt_get(h) : 0u;
         simt::syncwarp(HCW_FULL);
         uint32_t idx = c0;
-        if (act) idx = (simt::atoms_add(w.sm, (h >> 1) * 4u, (h & 1u) ? 0x10000u : 1u) >> ((h & 1u) * 16u)) & 0xFFFFu;
+        if (act) idx = w.cnt_add(h);
         uint32_t pend = simt::ballot(HCW_FULL, act && idx != c0);
         while (pend) {
             const uint32_t hl = simt::shfl(HCW_FULL, h, simt::ffs(pend) - 1);
@@ -127,7 +168,7 @@ SIMT_DEV void hcw_build(const Hcw& w)
 }
 
 // the block's bytes into shared memory (aligned 16-byte reads of words that hold at least one input byte)
-SIMT_DEV void hcw_stage(const Hcw& w)
+SIMT_DEV void hcw_stage(const Hcw<true>& w)
 {
     for (uint32_t i = (uint32_t)w.lane * 16u; i < (uint32_t)w.n; i += 512u) {
         const uintptr_t a = (uintptr_t)(w.src + i), al = a & ~(uintptr_t)15;
@@ -151,11 +192,11 @@ struct HcwHit { int len, ref, start, repl, delta; };
 // r = rank[q].  Candidate k is sorted[r-1-k] while that entry is in q's bucket, then position 0, then nothing; at most 256
 // are examined (:403, :471), one more when the first one lies within 4 bytes (:411-420 consumes it without an attempt).
 // The reference's byte filters (:426, :480) only skip candidates that cannot win; the 4-byte test implies them.
-template <bool WIDER>
-SIMT_DEV HcwHit hcw_search(const Hcw& w, int q, int r, int start_limit, int longest)
+template <bool WIDER, bool SMEM>
+SIMT_DEV HcwHit hcw_search(const Hcw<SMEM>& w, int q, int r, int start_limit, int longest)
 {
     const int lane = w.lane;
-    const uint32_t vq = hcw_sm32(w, (uint32_t)q), h = hcw_hash(vq);
+    const uint32_t vq = w.rd32((uint32_t)q), h = hcw_hash(vq);
     uint32_t best = 0, best_c = 0, best_back = 0;
     int K = 256;
     HcwHit out{0, 0, 0, 0, 0};
@@ -173,7 +214,7 @@ SIMT_DEV HcwHit hcw_search(const Hcw& w, int q, int r, int start_limit, int long
             const int k = 32 * (b0 + j) + lane, idx = r - 1 - k;
             uint32_t c = cc[j], vc = 0;
             bool inb = false;
-            if (idx >= 0 && k < K) { vc = hcw_sm32(w, c); inb = hcw_hash(vc) == h; }
+            if (idx >= 0 && k < K) { vc = w.rd32(c); inb = hcw_hash(vc) == h; }
             const uint32_t outm = simt::ballot(HCW_FULL, !inb);
             const int first_out = outm ? simt::ffs(outm) - 1 : 32;
             bool valid = lane < first_out;
@@ -187,7 +228,7 @@ SIMT_DEV HcwHit hcw_search(const Hcw& w, int q, int r, int start_limit, int long
                 uint32_t len = 4u + (uint32_t)hcw_common(w, q + 4, (int)c + 4, w.matchlimit);
                 if (WIDER) {
                     while (q - (int)back > start_limit && (int)c - (int)back > 0 &&
-                           simt::lds_u8(w.sm, (uint32_t)q - back - 1u) == simt::lds_u8(w.sm, c - back - 1u)) back++;      // :505
+                           w.rd8((uint32_t)q - back - 1u) == w.rd8(c - back - 1u)) back++;      // :505
                     len += back;
                 }
                 key = len * 512u + (511u - (uint32_t)k);                  // longest first, then earliest in the walk
@@ -223,7 +264,8 @@ SIMT_DEV HcwHit hcw_search(const Hcw& w, int q, int r, int start_limit, int long
 // such candidate yields >= 4, :428-431) or -1, and that position's rank.
 struct HcwScan { int off, rank; };
 
-SIMT_DEV HcwScan hcw_scan(const Hcw& w, int ip)
+template <bool SMEM>
+SIMT_DEV HcwScan hcw_scan(const Hcw<SMEM>& w, int ip)
 {
     const int lane = w.lane;
     int q[2], r[2]; bool act[2];
@@ -240,7 +282,7 @@ SIMT_DEV HcwScan hcw_scan(const Hcw& w, int ip)
     HcwScan res{-1, 0};
 #pragma unroll
     for (int s = 0; s < 2; s++) {
-        const uint32_t vq = act[s] ? hcw_sm32(w, (uint32_t)q[s]) : 0u, h = hcw_hash(vq);
+        const uint32_t vq = act[s] ? w.rd32((uint32_t)q[s]) : 0u, h = hcw_hash(vq);
         int k = 0, K = 256;
         bool done = !act[s], hit = false;
         for (;;) {
@@ -250,7 +292,7 @@ SIMT_DEV HcwScan hcw_scan(const Hcw& w, int ip)
                     const int idx = r[s] - 1 - k;
                     uint32_t c = cand[s][t], vc = 0;
                     bool inb = false;
-                    if (idx >= 0) { vc = hcw_sm32(w, c); inb = hcw_hash(vc) == h; }
+                    if (idx >= 0) { vc = w.rd32(c); inb = hcw_hash(vc) == h; }
                     if (!inb) { c = 0; vc = w.v0; }
                     if (k == 0 && (int)c >= q[s] - 4) K = 257;
                     if (vc == vq) { hit = true; done = true; }
@@ -286,13 +328,22 @@ SIMT_DEV int hcw_put_len(const HcwOut& o, int at, int v)               // 255, 2
     return at + n255 + 1;
 }
 
-SIMT_DEV bool hcw_emit(const Hcw& w, HcwOut& o, int ml, int ref)       // :521-550 LZ4_encodeSequence; true = output full
+// the literals [at, at+n) of the block -> dst (the caller has checked that they fit)
+template <bool SMEM>
+SIMT_DEV void hcw_literals(const Hcw<SMEM>& w, uint8_t* dst, int at, int n)
+{
+    if (SMEM) group_copy<32, false>(dst, HcwSmemSrc{w.sm, (uint32_t)at}, (uint32_t)n, w.lane, HCW_FULL);
+    else      group_copy<32, false>(dst, HcwInputSrc{w.src + at}, (uint32_t)n, w.lane, HCW_FULL);
+}
+
+template <bool SMEM>
+SIMT_DEV bool hcw_emit(const Hcw<SMEM>& w, HcwOut& o, int ml, int ref)       // :521-550 LZ4_encodeSequence; true = output full
 {
     const int L = o.ip - o.anchor, tok = o.op++;
     uint32_t tv;
     if (o.op + L + 8 + (L >> 8) > o.cap) return true;                  // :529 (token, length bytes, literals and offset fit from here on)
     if (L >= 15) { tv = 0xF0; o.op = hcw_put_len(o, o.op, L - 15); } else tv = (uint32_t)L << 4;
-    group_copy<32, false>(o.dst + o.op, HcwSmemSrc{w.sm, (uint32_t)o.anchor}, (uint32_t)L, w.lane, HCW_FULL);
+    hcw_literals(w, o.dst + o.op, o.anchor, L);
     o.op += L;
     o.put(o.op, (uint32_t)(o.ip - ref) & 255); o.put(o.op + 1, ((uint32_t)(o.ip - ref) >> 8) & 255); o.op += 2;
     const int len = ml - 4;
@@ -303,17 +354,19 @@ SIMT_DEV bool hcw_emit(const Hcw& w, HcwOut& o, int ml, int ref)       // :521-5
     return false;
 }
 
-// One block, all 32 lanes.  `sm` = HCW_SMEM_BYTES of shared memory, `index` = this warp's HCW_INDEX_BYTES.
+// One block, all 32 lanes.  `sm` = HCW_SMEM_BYTES of shared memory (SMEM variant), `index` = this warp's HCW_INDEX_BYTES.
 // Returns the bytes written, 0 = did not fit, HCW_FALLBACK = not for this kernel (the same value in every lane).
+template <bool SMEM>
 SIMT_DEV int hcw_encode_block(simt::smem_ref sm, void* index, const uint8_t* src, int n, uint8_t* dst, int cap, int lane)
 {
     if (n < 0 || cap < 0) return 0;
     if (n > HCW_MAX_BLOCK) return HCW_FALLBACK;
-    Hcw w; w.sm = sm; w.rank = (uint16_t*)index; w.sorted = w.rank + 65536; w.src = src; w.n = n; w.lane = lane;
+    Hcw<SMEM> w; w.sm = sm; w.rank = (uint16_t*)index; w.sorted = w.rank + 65536; w.cnt = (uint32_t*)(w.sorted + 65536);
+    w.src = src; w.n = n; w.lane = lane; w.in.init(src);
     w.mflimit = n - 12; w.matchlimit = n - 5;
     if (w.mflimit > 1) hcw_build(w);
-    hcw_stage(w);
-    w.v0 = n >= 4 ? hcw_sm32(w, 0) : 0u;
+    if constexpr (SMEM) hcw_stage(w);
+    w.v0 = n >= 4 ? w.rd32(0) : 0u;
     HcwOut o{dst, cap, 0, 1, 0, lane};                                 // :581 ip = 1
     const int mflimit = w.mflimit, matchlimit = w.matchlimit;
     (void)matchlimit;
@@ -326,7 +379,7 @@ SIMT_DEV int hcw_encode_block(simt::smem_ref sm, void* index, const uint8_t* src
     do {                                                                                                         \
         const int q__ = (q_);                                                                                    \
         if (q__ < next) odd = true; else next = q__;                                                             \
-        const HcwHit h__ = hcw_search<true>(w, q__, (int)simt::ldg_u16(w.rank + q__), (lim_), (longest_));      \
+        const HcwHit h__ = hcw_search<true, SMEM>(w, q__, (int)simt::ldg_u16(w.rank + q__), (lim_), (longest_));      \
         ML_ = h__.len; if (h__.len > (longest_)) { REF_ = h__.ref; START_ = h__.start; }                         \
     } while (0)
 
@@ -337,11 +390,11 @@ SIMT_DEV int hcw_encode_block(simt::smem_ref sm, void* index, const uint8_t* src
         o.ip += sc.off;
         next = o.ip;
         {
-            const HcwHit b = hcw_search<false>(w, o.ip, sc.rank, 0, 0);
+            const HcwHit b = hcw_search<false, SMEM>(w, o.ip, sc.rank, 0, 0);
             ml = b.len; ref = b.ref;
             if (b.repl) {                                              // :437-455: chain[ip..end) := delta, nextToUpdate = end
                 if (b.delta >= 2) {                                    // equal to the static chain unless two of the period's strings share a hash
-                    const uint32_t hj = lane < b.delta ? hcw_hash(hcw_sm32(w, (uint32_t)(o.ip - b.delta + lane))) : 0x10000u + (uint32_t)lane;
+                    const uint32_t hj = lane < b.delta ? hcw_hash(w.rd32((uint32_t)(o.ip - b.delta + lane))) : 0x10000u + (uint32_t)lane;
                     const uint32_t h0 = simt::shfl(HCW_FULL, hj, 0), h1 = simt::shfl(HCW_FULL, hj, 1), h2 = simt::shfl(HCW_FULL, hj, 2), h3 = simt::shfl(HCW_FULL, hj, 3);
                     if (h0 == h1 || h0 == h2 || h0 == h3 || h1 == h2 || h1 == h3 || h2 == h3) odd = true;
                 }
@@ -410,7 +463,7 @@ SIMT_DEV int hcw_encode_block(simt::smem_ref sm, void* index, const uint8_t* src
         const int R = n - o.anchor;
         if ((uint32_t)(o.op + R + 1 + (R + 255 - 15) / 255) > (uint32_t)cap) return 0;
         if (R >= 15) { o.put(o.op++, 0xF0); o.op = hcw_put_len(o, o.op, R - 15); } else o.put(o.op++, (uint32_t)R << 4);
-        group_copy<32, false>(dst + o.op, HcwSmemSrc{w.sm, (uint32_t)o.anchor}, (uint32_t)R, lane, HCW_FULL);
+        hcw_literals(w, dst + o.op, o.anchor, R);
         o.op += R;
     }
     return o.op;

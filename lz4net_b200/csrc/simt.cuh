@@ -84,6 +84,7 @@ SIMT_DEV void cp_async16(smem_ref r, uint32_t off, const void* g) { asm volatile
 SIMT_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> SIMT_DEV void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 SIMT_DEV uint32_t atomic_inc(uint32_t* p) { return atomicAdd(p, 1u); }
+SIMT_DEV uint32_t atomg_add(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }              // global memory, returns the old word
 
 // software prefetch of the line holding *p (no destination register, never faults the warp's progress)
 SIMT_DEV void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }

@@ -111,19 +111,19 @@ def encode_hc(block, cap=None, src_skew=0):
 HCW_FALLBACK = -2 ** 31
 
 
-def encode_hcw(block, cap=None, src_skew=0, dst_skew=0, sched_seed=1):
+def encode_hcw(block, cap=None, src_skew=0, dst_skew=0, sched_seed=1, smem=True):
     """The warp-per-block HC encoder (lz4hc_warp.cuh).  Returns (result, bytes); result == HCW_FALLBACK when the kernel hands
     the block to the thread-per-block one."""
     n = len(block)
     if cap is None:
         cap = n + n // 255 + 16
-    a = np.zeros(src_skew + n + 64, np.uint8)
+    a = np.zeros(src_skew + n + 64, np.uint8)            # smem: block staged in shared memory; else read through the read-only path
     a[src_skew:src_skew + n] = np.frombuffer(block, np.uint8)
     lo = 32 + dst_skew
     d = np.full(max(cap, 0) + 96 + dst_skew, 0xCD, np.uint8)
     f = lib().emu_encode_hcw
     f.restype = C.c_int
-    r = f(C.c_void_p(a.ctypes.data + src_skew), n, C.c_void_p(d.ctypes.data + lo), cap, C.c_uint64(sched_seed))
+    r = f(C.c_void_p(a.ctypes.data + src_skew), n, C.c_void_p(d.ctypes.data + lo), cap, C.c_uint64(sched_seed), int(smem))
     assert (d[:lo] == 0xCD).all() and (d[lo + max(cap, 0):] == 0xCD).all(), "HC warp encoder wrote outside [dst, dst+cap)"
     return int(r), d[lo:lo + max(r, 0)].tobytes()
 

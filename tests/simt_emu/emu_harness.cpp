@@ -134,16 +134,17 @@ int emu_encode_hc(const uint8_t* src, int n, uint8_t* dst, int cap)
 }
 
 // the warp-per-block HC encoder (static index); returns HCW_FALLBACK when the block is handed to the scalar kernel
-struct HcwJob { const uint8_t* src; int n; uint8_t* dst; int cap; int result; void* sm; void* index; };
+struct HcwJob { const uint8_t* src; int n; uint8_t* dst; int cap; int result; void* sm; void* index; int smem; };
 static void hcw_entry(int lane, void* arg)
 {
     HcwJob* j = (HcwJob*)arg;
-    const int r = hcw_encode_block(simt::smem_ref_of(j->sm), j->index, j->src, j->n, j->dst, j->cap, lane);
+    const int r = j->smem ? hcw_encode_block<true>(simt::smem_ref_of(j->sm), j->index, j->src, j->n, j->dst, j->cap, lane)
+                          : hcw_encode_block<false>(simt::smem_ref_of(j->sm), j->index, j->src, j->n, j->dst, j->cap, lane);
     if (lane == 0) j->result = r;
 }
-int emu_encode_hcw(const uint8_t* src, int n, uint8_t* dst, int cap, uint64_t sched_seed)
+int emu_encode_hcw(const uint8_t* src, int n, uint8_t* dst, int cap, uint64_t sched_seed, int smem)
 {
-    HcwJob j{src, n, dst, cap, 0, aligned_alloc(16, HCW_SMEM_BYTES), aligned_alloc(16, HCW_INDEX_BYTES)};
+    HcwJob j{src, n, dst, cap, 0, aligned_alloc(16, HCW_SMEM_BYTES), aligned_alloc(16, HCW_INDEX_BYTES), smem};
     memset(j.sm, 0x5A, HCW_SMEM_BYTES); memset(j.index, 0xA5, HCW_INDEX_BYTES);     // stale garbage, like a reused slot
     simt_emu::run_warp(hcw_entry, &j, sched_seed);
     free(j.sm); free(j.index);
