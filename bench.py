@@ -684,14 +684,29 @@ def main():
         for cls in ("E50", "ETEXT"):
             # (ETEXT gains nothing from more than 65 536 blocks in flight: half the batch keeps the default run short)
             w = Workload(ctx, min(args.hc_blocks if cls == "E50" else args.hc_blocks // 2, args.blocks), cls, args.wave, seed=3)
+            # the library's default HC kernel first (its output is what the round trip below checks), then the others
+            # (hc_kernel 0: a thread per block; 1 / 2: a warp per block on a static index, block in shared memory / through L1)
+            default_kernel = ctx.get_option("hc_kernel")
             te, _ = measure_pair(w, 1, 1, hc=True)
             torch.cuda.synchronize()
             cs = int(w.clen.sum()); rb = w.n * BLOCK
             for wv in range(w.n_waves):
                 b0, b1 = w.decode_wave(wv); torch.cuda.synchronize()
                 assert torch.equal(w.out[: (b1 - b0) * BLOCK], w.raw[b0 * BLOCK: b1 * BLOCK]), "HC round trip failed"
-            hc[cls] = {"ratio": round(cs / rb, 4), "encode_gbs": round(rb / te / GB, 2), "blocks": w.n,
-                       "roofline_frac": round((rb + cs) / te / GB / peak_hbm, 5)}
+            hc[cls] = {"ratio": round(cs / rb, 4), "encode_gbs": round(rb / te / GB, 2), "blocks": w.n, "hc_kernel": default_kernel,
+                       "roofline_frac": round((rb + cs) / te / GB / peak_hbm, 5), "kernels": {}}
+            lens_default = w.clen.clone()
+            for k in (0, 1, 2):
+                if k == default_kernel:
+                    hc[cls]["kernels"][str(k)] = hc[cls]["encode_gbs"]; continue
+                ctx.set_option("hc_kernel", k)
+                try:
+                    tk, _ = measure_pair(w, 1, 1, hc=True)
+                    torch.cuda.synchronize()
+                    assert torch.equal(w.clen, lens_default), "HC kernels disagree on the compressed lengths"
+                    hc[cls]["kernels"][str(k)] = round(rb / tk / GB, 2)
+                finally:
+                    ctx.set_option("hc_kernel", default_kernel)
             if not args.no_cpu:
                 hc[cls]["cpu_reference_gbs"] = round(cpu_hc(cls, 1024 if cls == "ETEXT" else 4096, os.cpu_count() or 1), 3)
             del w; torch.cuda.empty_cache()

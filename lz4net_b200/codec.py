@@ -49,6 +49,11 @@ class Context:
     def set_option(self, key: str, value: int):
         native.check(native.lib().lz4b200_set_option(self._h, key.encode(), int(value)), f"set_option({key})")
 
+    def get_option(self, key: str) -> int:
+        v = native._L(0)
+        native.check(native.lib().lz4b200_get_option(self._h, key.encode(), native.C.byref(v)), f"get_option({key})")
+        return int(v.value)
+
     def synchronize(self):
         native.check(native.lib().lz4b200_synchronize(self._h), "synchronize")
 

@@ -622,6 +622,21 @@ int lz4b200_set_option(lz4b200_ctx* c, const char* key, int64_t value)
     return LZ4B200_OK;
 }
 
+int lz4b200_get_option(lz4b200_ctx* c, const char* key, int64_t* value)
+{
+    if (!c || !key || !value) return fail(LZ4B200_E_ARG, "bad argument");
+    std::lock_guard<std::mutex> lock(c->mu);
+    const std::string k(key);
+    if (k == "hc_kernel") *value = c->hc_kernel;
+    else if (k == "hc_warps_per_sm") *value = c->hc_warps_per_sm;
+    else if (k == "hc_concurrency") *value = c->hc_concurrency;
+    else if (k == "decode_lanes") *value = c->decode_lanes_auto ? 0 : c->decode_lanes;
+    else if (k == "encode_variant") *value = c->encode_variant;
+    else if (k == "encode_ctas_per_sm") *value = c->encode_ctas_per_sm;
+    else return fail(LZ4B200_E_ARG, "unknown option");
+    return LZ4B200_OK;
+}
+
 int64_t lz4b200_launch_count(lz4b200_ctx* c) { return c ? c->launches : 0; }
 
 int lz4b200_host_register(void* ptr, int64_t bytes)

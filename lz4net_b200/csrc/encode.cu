@@ -105,14 +105,13 @@ cudaError_t launch_encode_hc(const BatchArgs& a, void* scratch, int concurrency,
     return cudaGetLastError();
 }
 
-constexpr int HCW_GLOBAL_MAX_WARPS = 32;                   // global variant: CTAs per SM the register budget is cut for
-
 // ---- HC encoder, blocks <= 64 KiB: one WARP per block on a static index (lz4hc_warp.cuh) -----------------------------
 // One 32-thread CTA per warp.  SMEM variant: the block's bytes take 64 KiB of shared memory, so at most three CTAs share an
 // SM (fewer are forced by asking for more shared memory than the CTA uses).  Global variant: no shared memory, up to 32
 // CTAs per SM, the block read through L1 / L2.  Each CTA owns HCW_INDEX_BYTES of the scratch arena (rank / sorted tables).
-template <bool SMEM>
-__global__ void __launch_bounds__(32, SMEM ? 3 : HCW_GLOBAL_MAX_WARPS)
+// MINB = CTAs per SM the register budget is cut for (SMEM: 3; global variant: 16 -> <= 128 registers, 32 -> 64)
+template <bool SMEM, int MINB>
+__global__ void __launch_bounds__(32, MINB)
 lz4_encode_hcw_kernel(BatchArgs a, uint8_t* arena, uint32_t* counter)
 {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -174,16 +173,21 @@ cudaError_t launch_encode_hcw(const BatchArgs& a, void* scratch, int variant, in
         // residency: the CTA needs HCW_SMEM_BYTES; asking for a larger share of the SM keeps the others out
         int dyn = HCW_SMEM_BYTES;
         if (warps < 3) { const int share = dev.smem_per_sm / warps - 2048; if (share > dyn) dyn = share < dev.smem_optin ? share : dev.smem_optin; }
-        e = cudaFuncSetAttribute(lz4_encode_hcw_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+        e = cudaFuncSetAttribute(lz4_encode_hcw_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
         if (e != cudaSuccess) return e;
-        lz4_encode_hcw_kernel<true><<<(unsigned)grid, 32, dyn, stream>>>(a, (uint8_t*)scratch, counter);
+        lz4_encode_hcw_kernel<true, 3><<<(unsigned)grid, 32, dyn, stream>>>(a, (uint8_t*)scratch, counter);
     } else {
         // all of the SM's on-chip memory as L1 (the blocks' bytes are re-read at random).  Residency below 32 CTAs per SM
         // is a matter of the grid alone: CTAs are placed breadth-first over the SMs and the kernel is persistent.
-        e = cudaFuncSetAttribute(lz4_encode_hcw_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
-        if (e != cudaSuccess) return e;
-        const int dyn = 0;
-        lz4_encode_hcw_kernel<false><<<(unsigned)grid, 32, dyn, stream>>>(a, (uint8_t*)scratch, counter);
+        if (warps <= 16) {
+            e = cudaFuncSetAttribute(lz4_encode_hcw_kernel<false, 16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+            if (e != cudaSuccess) return e;
+            lz4_encode_hcw_kernel<false, 16><<<(unsigned)grid, 32, 0, stream>>>(a, (uint8_t*)scratch, counter);
+        } else {
+            e = cudaFuncSetAttribute(lz4_encode_hcw_kernel<false, 32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+            if (e != cudaSuccess) return e;
+            lz4_encode_hcw_kernel<false, 32><<<(unsigned)grid, 32, 0, stream>>>(a, (uint8_t*)scratch, counter);
+        }
     }
     if (launches) ++*launches;
     e = cudaGetLastError();

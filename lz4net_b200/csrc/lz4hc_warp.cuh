@@ -78,9 +78,9 @@ struct Hcw {
     SIMT_MEM uint32_t cnt_get(uint32_t h) const
     {
         if (SMEM) return simt::lds_u16(sm, h * 2u);
-        return (simt::ldg_u32(cnt + (h >> 1)) >> ((h & 1u) * 16u)) & 0xFFFFu;
+        return (simt::ldg_cg_u32(cnt + (h >> 1)) >> ((h & 1u) * 16u)) & 0xFFFFu;        // (L2: the word is modified by atomics)
     }
-    SIMT_MEM uint32_t cnt_word(uint32_t wi) const { return SMEM ? simt::lds_u32(sm, wi * 4u) : simt::ldg_u32(cnt + wi); }
+    SIMT_MEM uint32_t cnt_word(uint32_t wi) const { return SMEM ? simt::lds_u32(sm, wi * 4u) : simt::ldg_cg_u32(cnt + wi); }
     SIMT_MEM void cnt_word_set(uint32_t wi, uint32_t v) const { if (SMEM) simt::sts_u32(sm, wi * 4u, v); else simt::stg_u32(cnt + wi, v); }
 };
 
@@ -98,6 +98,27 @@ SIMT_DEV int hcw_common(const Hcw<SMEM>& w, int a, int b, int limit)
     }
     while (a < limit && w.rd8((uint32_t)a) == w.rd8((uint32_t)b)) { a++; b++; }
     return a - a0;
+}
+
+// the same count by the whole warp for ONE pair (a, b, limit identical in every lane): 128 bytes per step, the first
+// differing word found with one vote.  Same value as hcw_common (the common prefix, capped at limit).
+template <bool SMEM>
+SIMT_DEV int hcw_common_warp(const Hcw<SMEM>& w, int a, int b, int limit)
+{
+    for (int done = 0; ; done += 128) {
+        const int pa = a + done + 4 * w.lane;
+        const bool in = pa + 4 <= limit;
+        const uint32_t x = in ? (w.rd32((uint32_t)pa) ^ w.rd32((uint32_t)(b + done + 4 * w.lane))) : 0u;
+        const uint32_t m = simt::ballot(HCW_FULL, !in || x != 0u);
+        if (m) {
+            const int f = simt::ffs(m) - 1;
+            const uint32_t xf = simt::shfl(HCW_FULL, x, f);
+            int t = a + done + 4 * f;                                  // (lane f's position)
+            if (t + 4 <= limit) return t - a + ((simt::ffs(xf) - 1) >> 3);
+            while (t < limit && w.rd8((uint32_t)t) == w.rd8((uint32_t)(b + t - a))) t++;     // fewer than four bytes left
+            return t - a;
+        }
+    }
 }
 
 // literal source: the staged block (position 0 at shared offset 0, so alignment = position alignment)
@@ -126,44 +147,68 @@ SIMT_DEV void hcw_build(const Hcw<SMEM>& w)
     const InWords& in = w.in;
     w.cnt_zero();
     simt::syncwarp(HCW_FULL);
-    // bucket sizes: u16 counters, two to a word, atomic adds on the word (a bucket never holds 65536 positions: no carry)
-    for (int base = 1; base < P; base += 32) {
-        const int p = base + lane;
-        if (p < P) w.cnt_add(hcw_hash(in.at(p)));
+    // bucket sizes: u16 counters, two to a word, atomic adds on the word (a bucket never holds 65536 positions: no carry).
+    // 128 positions per iteration, their input words requested together; the hashes are parked in rank[] for the scatter.
+    for (int base = 1; base < P; base += 128) {
+        InWords::Raw raw[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) { const int p = base + 32 * j + lane; if (p < P) raw[j] = in.raw<0>(p); }      // p <= n - 13: both words hold input bytes
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int p = base + 32 * j + lane;
+            if (p < P) { const uint32_t h = hcw_hash(InWords::word(raw[j])); simt::stg_u16(w.rank + p, h); w.cnt_add(h); }
+        }
     }
     simt::syncwarp(HCW_FULL);
-    // exclusive prefix sum in place: counter -> first index of the bucket
+    // exclusive prefix sum in place: counter -> first index of the bucket.  Eight counters (four words) per lane and
+    // iteration: lane-local prefix, one warp scan of the lane totals.
     uint32_t carry = 0;
-    for (uint32_t w0 = 0; w0 < 16384u; w0 += 32u) {
-        const uint32_t v = w.cnt_word(w0 + lane), lo = v & 0xFFFFu, hi = v >> 16, s = lo + hi;
+    for (uint32_t w0 = 0; w0 < 16384u; w0 += 128u) {
+        const uint32_t wi = w0 + 4u * (uint32_t)lane;
+        uint32_t v[4], s = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) { v[j] = w.cnt_word(wi + j); s += (v[j] & 0xFFFFu) + (v[j] >> 16); }
         uint32_t x = s;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { const uint32_t y = simt::shfl(HCW_FULL, x, lane >= d ? lane - d : lane); if (lane >= d) x += y; }
-        const uint32_t excl = x - s + carry;
-        w.cnt_word_set(w0 + lane, (excl & 0xFFFFu) | ((excl + lo) << 16));
+        uint32_t run = x - s + carry;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t lo = v[j] & 0xFFFFu, hi = v[j] >> 16;
+            w.cnt_word_set(wi + j, (run & 0xFFFFu) | ((run + lo) << 16));
+            run += lo + hi;
+        }
         carry += simt::shfl(HCW_FULL, x, 31);
     }
     simt::syncwarp(HCW_FULL);
-    // stable scatter, 32 consecutive positions per step.  Lanes that share a hash inside one step get their indices from
-    // the ATOMS in no particular order: such a step (one lane sees a counter that is not the value every lane read before)
-    // re-ranks the sharing lanes by position.
-    for (int base = 1; base < P; base += 32) {
-        const int p = base + lane;
-        const bool act = p < P;
-        const uint32_t h = act ? hcw_hash(in.at(p)) : 0xFFFFFFFFu;
-        const uint32_t c0 = act ? w.cnt_get(h) : 0u;
-        simt::syncwarp(HCW_FULL);
-        uint32_t idx = c0;
-        if (act) idx = w.cnt_add(h);
-        uint32_t pend = simt::ballot(HCW_FULL, act && idx != c0);
-        while (pend) {
-            const uint32_t hl = simt::shfl(HCW_FULL, h, simt::ffs(pend) - 1);
-            const uint32_t same = simt::ballot(HCW_FULL, h == hl);
-            if (h == hl) idx = c0 + (uint32_t)simt::popc(same & ((1u << lane) - 1u));
-            pend &= ~same;
+    // stable scatter, 32 consecutive positions per step (eight steps' hashes requested together).  Lanes that share a hash
+    // inside one step get their indices from the atomic in no particular order: such a step (one lane sees a counter that
+    // is not the value every lane read before) re-ranks the sharing lanes by position.
+    for (int base8 = 1; base8 < P; base8 += 256) {
+        uint32_t hh[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) { const int p = base8 + 32 * j + lane; hh[j] = p < P ? simt::ldg_u16(w.rank + p) : 0xFFFFFFFFu; }
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int base = base8 + 32 * j;
+            if (base >= P) break;
+            const int p = base + lane;
+            const bool act = p < P;
+            const uint32_t h = hh[j];
+            const uint32_t c0 = act ? w.cnt_get(h) : 0u;
+            simt::syncwarp(HCW_FULL);
+            uint32_t idx = c0;
+            if (act) idx = w.cnt_add(h);
+            uint32_t pend = simt::ballot(HCW_FULL, act && idx != c0);
+            while (pend) {
+                const uint32_t hl = simt::shfl(HCW_FULL, h, simt::ffs(pend) - 1);
+                const uint32_t same = simt::ballot(HCW_FULL, h == hl);
+                if (h == hl) idx = c0 + (uint32_t)simt::popc(same & ((1u << lane) - 1u));
+                pend &= ~same;
+            }
+            if (act) { simt::stg_u16(w.sorted + idx, (uint32_t)p); simt::stg_u16(w.rank + p, idx); }
+            simt::syncwarp(HCW_FULL);
         }
-        if (act) { simt::stg_u16(w.sorted + idx, (uint32_t)p); simt::stg_u16(w.rank + p, idx); }
-        simt::syncwarp(HCW_FULL);
     }
 }
 
@@ -208,11 +253,10 @@ SIMT_DEV HcwHit hcw_search(const Hcw<SMEM>& w, int q, int r, int start_limit, in
             cc[j] = (idx >= 0 && 32 * (b0 + j) + lane < 257) ? simt::ldg_u16(w.sorted + idx) : 0u;
         }
         bool ended = false;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            if (ended) break;
+#pragma unroll 1
+        for (int j = 0; j < 4 && !ended; j++) {                           // (one copy of the scoring code: the kernel is large enough)
             const int k = 32 * (b0 + j) + lane, idx = r - 1 - k;
-            uint32_t c = cc[j], vc = 0;
+            uint32_t c = j == 0 ? cc[0] : (j == 1 ? cc[1] : (j == 2 ? cc[2] : cc[3])), vc = 0;
             bool inb = false;
             if (idx >= 0 && k < K) { vc = w.rd32(c); inb = hcw_hash(vc) == h; }
             const uint32_t outm = simt::ballot(HCW_FULL, !inb);
@@ -224,11 +268,36 @@ SIMT_DEV HcwHit hcw_search(const Hcw<SMEM>& w, int q, int r, int start_limit, in
                 if (c_first >= q - 4) K = 257;
             }
             uint32_t key = 0, back = 0;
-            if (valid && vc == vq) {
+            const bool eq = valid && vc == vq;
+            const uint32_t eqm = simt::ballot(HCW_FULL, eq);
+            if (eqm && !(eqm & (eqm - 1u))) {
+                // one matching candidate in the batch (sparse data): the whole warp counts its length, 128 bytes a step
+                const int f = simt::ffs(eqm) - 1;
+                const int cf = (int)simt::shfl(HCW_FULL, c, f);
+                uint32_t len = 4u + (uint32_t)hcw_common_warp(w, q + 4, cf + 4, w.matchlimit);
+                if (WIDER) {                                              // :505 backwards, a lane per byte
+                    int lim = q - start_limit; if (cf < lim) lim = cf;    // steps allowed: startt > startLimit, reft > base
+                    uint32_t bk = 0;
+                    for (int done = 0; done < lim; done += 32) {
+                        const int i = done + w.lane;
+                        const bool ok = i < lim && w.rd8((uint32_t)(q - 1 - i)) == w.rd8((uint32_t)(cf - 1 - i));
+                        const uint32_t bad = simt::ballot(HCW_FULL, !ok);
+                        if (bad) { bk = (uint32_t)(done + simt::ffs(bad) - 1); break; }
+                        bk = (uint32_t)(done + 32);
+                    }
+                    back = bk; len += bk;
+                }
+                if (eq) key = len * 512u + (511u - (uint32_t)k);
+            } else if (eq) {
                 uint32_t len = 4u + (uint32_t)hcw_common(w, q + 4, (int)c + 4, w.matchlimit);
-                if (WIDER) {
-                    while (q - (int)back > start_limit && (int)c - (int)back > 0 &&
-                           w.rd8((uint32_t)q - back - 1u) == w.rd8(c - back - 1u)) back++;      // :505
+                if (WIDER) {                                              // :505 backwards, four bytes at a time
+                    int lim = q - start_limit; if ((int)c < lim) lim = (int)c;          // steps allowed: startt > startLimit, reft > base
+                    bool open = true;
+                    while (open && (int)back + 4 <= lim) {
+                        const uint32_t x = w.rd32((uint32_t)q - back - 4u) ^ w.rd32(c - back - 4u);
+                        if (x) { back += (uint32_t)simt::clz(x) >> 3; open = false; } else back += 4u;
+                    }
+                    while (open && (int)back < lim && w.rd8((uint32_t)q - back - 1u) == w.rd8(c - back - 1u)) back++;
                     len += back;
                 }
                 key = len * 512u + (511u - (uint32_t)k);                  // longest first, then earliest in the walk
@@ -328,12 +397,25 @@ SIMT_DEV int hcw_put_len(const HcwOut& o, int at, int v)               // 255, 2
     return at + n255 + 1;
 }
 
-// the literals [at, at+n) of the block -> dst (the caller has checked that they fit)
+// the literals [at, at+n) of the block -> dst (the caller has checked that they fit).  Runs of HC sequences are short:
+// byte steps inline; the 128-bit mover (incompressible stretches, the last literals) is ONE out-of-line copy of its code.
+SIMT_NOINLINE void hcw_copy_long_smem(uint8_t* dst, simt::smem_ref sm, uint32_t at, uint32_t n, int lane)
+{
+    group_copy<32, false>(dst, HcwSmemSrc{sm, at}, n, lane, HCW_FULL);
+}
+SIMT_NOINLINE void hcw_copy_long_input(uint8_t* dst, const uint8_t* src, uint32_t n, int lane)
+{
+    group_copy<32, false>(dst, HcwInputSrc{src}, n, lane, HCW_FULL);
+}
 template <bool SMEM>
 SIMT_DEV void hcw_literals(const Hcw<SMEM>& w, uint8_t* dst, int at, int n)
 {
-    if (SMEM) group_copy<32, false>(dst, HcwSmemSrc{w.sm, (uint32_t)at}, (uint32_t)n, w.lane, HCW_FULL);
-    else      group_copy<32, false>(dst, HcwInputSrc{w.src + at}, (uint32_t)n, w.lane, HCW_FULL);
+    if (n < 64) {
+        for (int i = w.lane; i < n; i += 32) simt::stg_u8(dst + i, (uint8_t)w.rd8((uint32_t)(at + i)));
+        return;
+    }
+    if (SMEM) hcw_copy_long_smem(dst, w.sm, (uint32_t)at, (uint32_t)n, w.lane);
+    else      hcw_copy_long_input(dst, w.src + at, (uint32_t)n, w.lane);
 }
 
 template <bool SMEM>
@@ -374,15 +456,6 @@ SIMT_DEV int hcw_encode_block(simt::smem_ref sm, void* index, const uint8_t* src
     int ml, ml2, ml3, ml0, ref = 0, ref2 = 0, ref3 = 0, ref0, start2 = 0, start3 = 0, start0;
     bool odd = false;                                                  // a state the static index does not describe
 
-    // LZ4HC_InsertAndGetWiderMatch at q
-#define HCW_WIDER(q_, lim_, longest_, ML_, REF_, START_)                                                        \
-    do {                                                                                                         \
-        const int q__ = (q_);                                                                                    \
-        if (q__ < next) odd = true; else next = q__;                                                             \
-        const HcwHit h__ = hcw_search<true, SMEM>(w, q__, (int)simt::ldg_u16(w.rank + q__), (lim_), (longest_));      \
-        ML_ = h__.len; if (h__.len > (longest_)) { REF_ = h__.ref; START_ = h__.start; }                         \
-    } while (0)
-
     while (o.ip < mflimit) {                                           // :584
         if (o.ip < next) return HCW_FALLBACK;
         const HcwScan sc = hcw_scan(w, o.ip);
@@ -404,24 +477,37 @@ SIMT_DEV int hcw_encode_block(simt::smem_ref sm, void* index, const uint8_t* src
         }
         if (odd || !ml) return HCW_FALLBACK;
         start0 = o.ip; ref0 = ref; ml0 = ml;                           // :589-592
+        // The look-ahead (:594-726) as a loop with ONE wider search per turn (one copy of the search code): a turn is
+        // either _Search2 or _Search3; _Search2 falling through into _Search3 is "next turn, _Search3".
         bool to_search2 = true;
         for (;;) {
+            int wq, wlim, wlong;
+            if (to_search2) { wq = o.ip + ml - 2; wlim = o.ip + 1; wlong = ml; }      // :595-597
+            else {                                                     // :628-646
+                if (start2 - o.ip < 18) {
+                    int new_ml = ml > 18 ? 18 : ml;
+                    if (o.ip + new_ml > start2 + ml2 - 4) new_ml = (start2 - o.ip) + ml2 - 4;
+                    const int corr = new_ml - (start2 - o.ip);
+                    if (corr > 0) { start2 += corr; ref2 += corr; ml2 -= corr; }
+                }
+                wq = start2 + ml2 - 3; wlim = start2; wlong = ml2;
+            }
+            int wml = wlong, wref = 0, wstart = 0;
+            if (wq + (to_search2 ? 2 : 3) < mflimit) {                 // "ip + ml < mflimit" / "start2 + ml2 < mflimit"
+                if (wq < next) return HCW_FALLBACK;
+                next = wq;
+                const HcwHit h = hcw_search<true, SMEM>(w, wq, (int)simt::ldg_u16(w.rank + wq), wlim, wlong);
+                wml = h.len; wref = h.ref; wstart = h.start;
+            }
             if (to_search2) {                                          // _Search2  :594-622
-                if (o.ip + ml < mflimit) HCW_WIDER(o.ip + ml - 2, o.ip + 1, ml, ml2, ref2, start2); else ml2 = ml;
-                if (odd) return HCW_FALLBACK;
+                ml2 = wml; if (wml > wlong) { ref2 = wref; start2 = wstart; }
                 if (ml2 == ml) { if (hcw_emit(w, o, ml, ref)) return 0; break; }
                 if (start0 < o.ip && start2 < o.ip + ml0) { o.ip = start0; ref = ref0; ml = ml0; }
                 if (start2 - o.ip < 3) { ml = ml2; o.ip = start2; ref = ref2; continue; }
+                to_search2 = false; continue;                          // on to _Search3
             }
-            // _Search3  :624-726
-            if (start2 - o.ip < 18) {
-                int new_ml = ml > 18 ? 18 : ml;
-                if (o.ip + new_ml > start2 + ml2 - 4) new_ml = (start2 - o.ip) + ml2 - 4;
-                const int corr = new_ml - (start2 - o.ip);
-                if (corr > 0) { start2 += corr; ref2 += corr; ml2 -= corr; }
-            }
-            if (start2 + ml2 < mflimit) HCW_WIDER(start2 + ml2 - 3, start2, ml2, ml3, ref3, start3); else ml3 = ml2;
-            if (odd) return HCW_FALLBACK;
+            // _Search3  :648-726
+            ml3 = wml; if (wml > wlong) { ref3 = wref; start3 = wstart; }
             if (ml3 == ml2) {                                          // :648-657 two sequences
                 if (start2 < o.ip + ml) ml = start2 - o.ip;
                 if (hcw_emit(w, o, ml, ref)) return 0;
@@ -442,7 +528,7 @@ SIMT_DEV int hcw_encode_block(simt::smem_ref sm, void* index, const uint8_t* src
                     to_search2 = true; continue;
                 }
                 start2 = start3; ref2 = ref3; ml2 = ml3;
-                to_search2 = false; continue;
+                continue;                                              // _Search3 again
             }
             if (start2 < o.ip + ml) {                                  // :695-714
                 if (start2 - o.ip < 15) {
@@ -455,10 +541,8 @@ SIMT_DEV int hcw_encode_block(simt::smem_ref sm, void* index, const uint8_t* src
             if (hcw_emit(w, o, ml, ref)) return 0;                     // :715
             o.ip = start2; ref = ref2; ml = ml2;
             start2 = start3; ref2 = ref3; ml2 = ml3;
-            to_search2 = false;
         }
     }
-#undef HCW_WIDER
     {                                                                  // :729-739 last literals
         const int R = n - o.anchor;
         if ((uint32_t)(o.op + R + 1 + (R + 255 - 15) / 255) > (uint32_t)cap) return 0;

@@ -85,6 +85,9 @@ SIMT_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "mem
 template <int N> SIMT_DEV void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 SIMT_DEV uint32_t atomic_inc(uint32_t* p) { return atomicAdd(p, 1u); }
 SIMT_DEV uint32_t atomg_add(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }              // global memory, returns the old word
+// load from L2, never from L1: for words that atomics modify (atomics are performed at L2; an L1 line filled by an earlier
+// load of the same word would be stale)
+SIMT_DEV uint32_t ldg_cg_u32(const uint32_t* p) { return __ldcg(p); }
 
 // software prefetch of the line holding *p (no destination register, never faults the warp's progress)
 SIMT_DEV void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }

@@ -47,6 +47,7 @@ SIGNATURES = {
     "lz4b200_host_unregister": (_I, [_P]),
     "lz4b200_synth_fill": (_I, [_P, _P, _L, C.c_int32, _I, _U64, _L, _P]),
     "lz4b200_set_option": (_I, [_P, C.c_char_p, _L]),
+    "lz4b200_get_option": (_I, [_P, C.c_char_p, C.POINTER(_L)]),
     "lz4b200_launch_count": (_L, [_P]),
 }
 

@@ -77,6 +77,7 @@ static inline void cp_async_commit() { cp_async_commit_emu(); }
 template <int N> static inline void cp_async_wait() { cp_async_wait_emu(N); }
 static inline uint32_t atomic_inc(uint32_t* p) { return (*p)++; }
 static inline uint32_t atomg_add(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
+static inline uint32_t ldg_cg_u32(const uint32_t* p) { return *p; }
 static inline void prefetch_l1(const void*) {}
 static inline void prefetch_l2(const void*) {}
 

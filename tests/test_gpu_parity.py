@@ -22,6 +22,16 @@ def ctx():
     return lz4net_b200.default_context()
 
 
+@pytest.fixture(params=[0, 1, 2], ids=["hc-thread", "hc-warp-smem", "hc-warp-l1"])
+def hck(ctx, request):
+    """Every HC kernel of the library (lz4hc_encode.cuh: a thread per block; lz4hc_warp.cuh: a warp per block on a static
+    index, block staged in shared memory / read through L1) emits the reference's bytes."""
+    prev = ctx.get_option("hc_kernel")
+    ctx.set_option("hc_kernel", request.param)
+    yield request.param
+    ctx.set_option("hc_kernel", prev)
+
+
 def _inputs(models=cases.MODELS, lens=None, seed0=0):
     lens = lens or ([65536] + cases.random_lengths(6, 65546, seed=77) + [65546, 13, 12, 1, 0, 300])
     out = []
@@ -70,7 +80,7 @@ def test_encode_output_limit_inside_every_emission_batch(ctx):
         assert (rr, o) == oracle.encode(d, cap=cap), cap
 
 
-def test_encode_hc_byte_identical(ctx):
+def test_encode_hc_byte_identical(ctx, hck):
     blocks = _inputs(lens=[65536, 40000, 65546, 20, 12, 0, 100000])
     res, outs = ctx.encode_blocks(blocks, hc=True)
     for b, r, o in zip(blocks, res, outs):
@@ -228,7 +238,37 @@ def test_device_batch_roundtrip_and_sampled_parity(ctx, cls):
         assert h_len[i] == r and h_packed[h_off[i]:h_off[i] + r].tobytes() == o, i
 
 
-def test_device_batch_hc_sampled_parity(ctx):
+def test_encode_hc_limited_output_every_kernel(ctx, hck):
+    blocks, caps = [], []
+    for i, m in enumerate(("ETEXT", "lowent", "E50", "periodic", "runs", "E0")):
+        d = cases.content(m, 5000, seed=40 + i).tobytes()
+        r = oracle.encode_hc(d)[0]
+        for cap in (r, r - 1, len(d), len(d) - 1, r // 2, 0, 1, 7, 8, 13):
+            blocks.append(d); caps.append(cap)
+    d = cases.content("ETEXT", 1200, seed=5).tobytes()
+    for cap in range(0, oracle.encode_hc(d)[0] + 3):
+        blocks.append(d); caps.append(cap)
+    res, outs = ctx.encode_blocks(blocks, caps=caps, hc=True)
+    for b, c, r, o in zip(blocks, caps, res, outs):
+        assert (r, o) == oracle.encode_hc(b, cap=c), (len(b), c)
+
+
+def test_encode_hc_handed_back_blocks(ctx, hck):
+    """A run of period 3 two of whose strings share a hash bucket (the warp kernels hand such a block to the thread kernel,
+    tests/test_kernels_emu.py) between ordinary blocks and blocks above 64 KiB: one batch, the reference's bytes."""
+    rng = np.random.default_rng(3)
+    odd = rng.integers(0, 256, 500, dtype=np.uint8).tobytes() + bytes([1, 65, 170]) * 200 + rng.integers(0, 256, 500, dtype=np.uint8).tobytes()
+    blocks = []
+    for i in range(40):
+        blocks.append(cases.content(cases.MODELS[i % len(cases.MODELS)], 65536 if i % 3 else 3000 + i, seed=900 + i).tobytes())
+        if i % 7 == 0: blocks.append(odd)
+        if i % 11 == 0: blocks.append(cases.content("ETEXT", 70000 + i, seed=i).tobytes())
+    res, outs = ctx.encode_blocks(blocks, hc=True)
+    for b, r, o in zip(blocks, res, outs):
+        assert (r, o) == oracle.encode_hc(b), len(b)
+
+
+def test_device_batch_hc_sampled_parity(ctx, hck):
     import torch
     from lz4net_b200 import batch, synth
     nb, bs = 1024, 65536
