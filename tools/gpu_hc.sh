@@ -5,7 +5,7 @@ set -u
 mkdir -p gpurun_out
 T0=$(date +%s)
 echo "=== pytest HC subset ==="
-timeout -s KILL 170 python -m pytest tests/test_gpu_parity.py -q -x -k "hc_byte_identical or hc_limited_output_every or hc_handed_back or device_batch_hc" 2>&1 | tail -8 | tee gpurun_out/pytest_hc.txt
+timeout -s KILL 170 python -m pytest tests/test_gpu_parity.py -q --timeout 80 -k "hc_byte_identical or hc_limited_output_every or hc_handed_back or device_batch_hc" 2>&1 | tail -8 | tee gpurun_out/pytest_hc.txt
 echo "elapsed $(( $(date +%s) - T0 )) s"
 echo "=== hc_ab ==="
 timeout -s KILL 170 python tools/hc_ab.py 120 2>&1 | tail -30 | tee gpurun_out/hc_ab.txt
