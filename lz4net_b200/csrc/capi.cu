@@ -119,7 +119,7 @@ struct lz4b200_ctx {
     int encode_tune[4] = {512, 12, 8, 24}; // prefetch distance, lane_copy_max, probe_max, wide_min (lz4_encode.cuh EncTune)
     size_t host_chunk_bytes = HOST_CHUNK_BYTES_DEFAULT;
     int hc_concurrency = 131072;         // blocks in flight (one thread each, 256 KiB state): 16384 / 65536 / 131072 / 262144 -> 2.8 / 8.3 / 9.7 / 9.7 GB/s (E50)
-    int hc_kernel = 0;                   // 0: one thread per block (any block size); one warp per block on a static index (blocks <= 64 KiB, the rest is handed to 0): 1 = block staged in shared memory, 2 = nothing in shared memory
+    int hc_kernel = -1;                  // -1: chosen per batch (encode.cu launch_encode_hc_auto); 0: one thread per block (any block size); one warp per block on a static index (blocks <= 64 KiB, the rest is handed to 0): 1 = block staged in shared memory, 2 = nothing in shared memory
     int hc_warps_per_sm = 0;             // warp kernels: blocks in flight per SM (0 = 3 for kernel 1, 16 for kernel 2)
     Slot slot[NSLOT];
     int64_t launches = 0;
@@ -155,14 +155,16 @@ int run_device(lz4b200_ctx* c, const BatchArgs& a, int op /*0 enc fast, 1 enc hc
     case 0: e = launch_encode_fast(a, c->counter(), c->encode_ctas_per_sm, c->encode_tune, c->encode_variant, c->dev, st, &c->launches); break;
     case 1: {
         const int conc = (int)std::min<int64_t>(c->hc_concurrency, std::max(a.n_blocks, 1));
-        const size_t need = c->hc_kernel ? hcw_scratch_bytes(a.n_blocks, c->hc_kernel, c->hc_warps_per_sm, c->dev) : hc_scratch_bytes(conc);
+        const size_t need = c->hc_kernel < 0 ? hc_auto_scratch_bytes(a.n_blocks, conc, c->dev)
+                          : (c->hc_kernel ? hcw_scratch_bytes(a.n_blocks, c->hc_kernel, c->hc_warps_per_sm, c->dev) : hc_scratch_bytes(conc));
         if (need > c->hc_arena.cap) {
             CU(cudaDeviceSynchronize());           // the arena may still be in use by an earlier launch
             CU(c->hc_arena.reserve(need));
         }
         // one arena per context: an HC launch may not overlap the previous one, whatever stream it was given
         CU(cudaStreamWaitEvent(st, c->hc_done, 0));
-        e = c->hc_kernel ? launch_encode_hcw(a, c->hc_arena.p, c->hc_kernel, c->hc_warps_per_sm, c->counter(), c->dev, st, &c->launches)
+        e = c->hc_kernel < 0 ? launch_encode_hc_auto(a, c->hc_arena.p, conc, c->counter(), c->dev, st, &c->launches)
+          : c->hc_kernel ? launch_encode_hcw(a, c->hc_arena.p, c->hc_kernel, c->hc_warps_per_sm, c->counter(), c->dev, st, &c->launches)
                               : launch_encode_hc(a, c->hc_arena.p, conc, c->counter(), c->dev, st, &c->launches);
         if (e == cudaSuccess) e = cudaEventRecord(c->hc_done, st);
         break;
@@ -615,7 +617,7 @@ int lz4b200_set_option(lz4b200_ctx* c, const char* key, int64_t value)
         c->hc_arena.release();
         c->hc_concurrency = (int)value;
     }
-    else if (k == "hc_kernel") { if (value < 0 || value > 2) return fail(LZ4B200_E_ARG, "hc_kernel must be 0 (thread per block), 1 or 2 (warp per block on a static index: block in shared memory / read through L1)"); c->hc_kernel = (int)value; }
+    else if (k == "hc_kernel") { if (value < -1 || value > 2) return fail(LZ4B200_E_ARG, "hc_kernel must be -1 (chosen per batch), 0 (thread per block), 1 or 2 (warp per block on a static index: block in shared memory / read through L1)"); c->hc_kernel = (int)value; }
     else if (k == "hc_warps_per_sm") { if (value < 0 || value > 32) return fail(LZ4B200_E_ARG, "hc_warps_per_sm must be 0..32"); c->hc_warps_per_sm = (int)value; }
     else if (k == "host_chunk_mb") { if (value < 1 || value > 4096) return fail(LZ4B200_E_ARG, "host_chunk_mb out of range"); c->host_chunk_bytes = (size_t)value << 20; }
     else return fail(LZ4B200_E_ARG, "unknown option");

@@ -73,8 +73,9 @@ cudaError_t launch_encode_fast(const BatchArgs& a, uint32_t* counter, int warps_
 constexpr int HC_THREADS = 32;
 
 __global__ void __launch_bounds__(HC_THREADS)
-lz4_encode_hc_kernel(BatchArgs a, uint8_t* arena, uint32_t* counter)
+lz4_encode_hc_kernel(BatchArgs a, uint8_t* arena, uint32_t* counter, const uint32_t* pick)
 {
+    if (pick && *pick != 0u) return;                       // auto mode: the pick kernel chose the warp kernel for this batch
     const size_t slot = (size_t)blockIdx.x * HC_THREADS + threadIdx.x;
     void* state = arena + slot * HC_STATE_BYTES;
     for (;;) {
@@ -90,19 +91,25 @@ size_t hc_scratch_bytes(int concurrency)
     return slots * HC_STATE_BYTES;
 }
 
+static cudaError_t launch_hc_threads(const BatchArgs& a, void* scratch, int concurrency, uint32_t* counter, const uint32_t* pick,
+                                     cudaStream_t stream, int64_t* launches)
+{
+    long long ctas = ((long long)concurrency + HC_THREADS - 1) / HC_THREADS;
+    long long want = ((long long)a.n_blocks + HC_THREADS - 1) / HC_THREADS;
+    if (ctas > want) ctas = want;
+    if (ctas < 1) ctas = 1;
+    lz4_encode_hc_kernel<<<(unsigned)ctas, HC_THREADS, 0, stream>>>(a, (uint8_t*)scratch, counter, pick);
+    if (launches) ++*launches;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_encode_hc(const BatchArgs& a, void* scratch, int concurrency, uint32_t* counter,
                              const DeviceInfo&, cudaStream_t stream, int64_t* launches)
 {
     if (a.n_blocks <= 0) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), stream);
     if (e != cudaSuccess) return e;
-    long long ctas = ((long long)concurrency + HC_THREADS - 1) / HC_THREADS;
-    long long want = ((long long)a.n_blocks + HC_THREADS - 1) / HC_THREADS;
-    if (ctas > want) ctas = want;
-    if (ctas < 1) ctas = 1;
-    lz4_encode_hc_kernel<<<(unsigned)ctas, HC_THREADS, 0, stream>>>(a, (uint8_t*)scratch, counter);
-    if (launches) ++*launches;
-    return cudaGetLastError();
+    return launch_hc_threads(a, scratch, concurrency, counter, nullptr, stream, launches);
 }
 
 // ---- HC encoder, blocks <= 64 KiB: one WARP per block on a static index (lz4hc_warp.cuh) -----------------------------
@@ -112,8 +119,9 @@ cudaError_t launch_encode_hc(const BatchArgs& a, void* scratch, int concurrency,
 // MINB = CTAs per SM the register budget is cut for (SMEM: 3; global variant: 16 -> <= 128 registers, 32 -> 64)
 template <bool SMEM, int MINB>
 __global__ void __launch_bounds__(32, MINB)
-lz4_encode_hcw_kernel(BatchArgs a, uint8_t* arena, uint32_t* counter)
+lz4_encode_hcw_kernel(BatchArgs a, uint8_t* arena, uint32_t* counter, const uint32_t* pick)
 {
+    if (pick && *pick == 0u) return;                       // auto mode: the pick kernel chose the thread kernel for this batch
     extern __shared__ __align__(16) uint8_t smem[];
     const simt::smem_ref sm = simt::smem_ref_of(smem);
     void* index = arena + (size_t)blockIdx.x * HCW_INDEX_BYTES;
@@ -126,6 +134,52 @@ lz4_encode_hcw_kernel(BatchArgs a, uint8_t* arena, uint32_t* counter)
         const int r = hcw_encode_block<SMEM>(sm, index, a.src + a.src_off[b], a.src_len[b], a.dst + a.dst_off[b], a.dst_cap[b], lane);
         if (lane == 0) a.out_len[b] = r;
         simt::syncwarp(0xFFFFFFFFu);                       // the next block reuses the shared memory and the index
+    }
+}
+
+// Auto mode, large batches: which kernel pays is a property of the data -- the index pays when chain walks are long.
+// A sample of the batch (up to 32 blocks, evenly spaced; one CTA each) is hashed into 15-bit buckets in shared memory;
+// depth = sum(min(c, 255) * c) / sum(c) over the buckets = the (clamped) bucket size an average position sees.
+// words: [0] block counter of the codec kernels (used as the ticket here and left zero), [1] pick (0 thread kernel,
+// 2 warp kernel), [2] sum(c), [3] sum(min(c,255)*c).
+constexpr int HC_PICK_SAMPLE = 32;
+constexpr uint32_t HC_PICK_DEPTH_X16 = 8 * 16;             // warp kernel from an average bucket size of 8
+
+__global__ void __launch_bounds__(256)
+lz4_hc_pick_kernel(BatchArgs a, uint32_t* words)
+{
+    extern __shared__ __align__(16) uint32_t buckets[];    // 16384 words of two u16 counters
+    const int nsample = gridDim.x;
+    const int b = (int)(((long long)blockIdx.x * a.n_blocks) / nsample);
+    const uint8_t* src = a.src + a.src_off[b];
+    int n = a.src_len[b];
+    const bool big = n > HCW_MAX_BLOCK;
+    if (n > HCW_MAX_BLOCK) n = HCW_MAX_BLOCK;
+    for (int i = threadIdx.x; i < 16384; i += blockDim.x) buckets[i] = 0;
+    __syncthreads();
+    for (int p = threadIdx.x; p + 4 <= n; p += blockDim.x) {
+        const uint32_t h = hcw_hash(in32(src, p));
+        atomicAdd(&buckets[h >> 1], (h & 1u) ? 0x10000u : 1u);
+    }
+    __syncthreads();
+    uint32_t s1 = 0, s2 = 0;
+    for (int i = threadIdx.x; i < 16384; i += blockDim.x) {
+        const uint32_t v = buckets[i], lo = v & 0xFFFFu, hi = v >> 16;
+        s1 += lo + hi; s2 += (lo < 255u ? lo : 255u) * lo + (hi < 255u ? hi : 255u) * hi;
+    }
+    for (int d = 16; d; d >>= 1) { s1 += __shfl_xor_sync(0xFFFFFFFFu, s1, d); s2 += __shfl_xor_sync(0xFFFFFFFFu, s2, d); }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&words[2], s1); atomicAdd(&words[3], s2 >> 4); }      // (s2 / 16: 32 blocks fit 32 bits)
+    if (big && threadIdx.x == 0) atomicAdd(&words[1], 1u);                  // blocks the warp kernel cannot take
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&words[0], 1u) == (uint32_t)nsample - 1u) {           // the last CTA decides
+            __threadfence();
+            const uint32_t t1 = atomicAdd(&words[2], 0u), t2 = atomicAdd(&words[3], 0u), nbig = atomicAdd(&words[1], 0u);
+            const bool deep = t1 && (unsigned long long)t2 * 256ull >= (unsigned long long)HC_PICK_DEPTH_X16 * t1;   // t2*16/t1 >= depth
+            atomicExch(&words[1], (deep && 2u * nbig < (uint32_t)nsample) ? 2u : 0u);
+            atomicExch(&words[0], 0u);
+        }
     }
 }
 
@@ -161,32 +215,30 @@ size_t hcw_scratch_bytes(int32_t n_blocks, int variant, int warps_per_sm, const 
 }
 
 // variant 1: block staged in shared memory (<= 3 warps per SM); 2: nothing in shared memory (<= 32 warps per SM)
-cudaError_t launch_encode_hcw(const BatchArgs& a, void* scratch, int variant, int warps_per_sm, uint32_t* counter,
-                              const DeviceInfo& dev, cudaStream_t stream, int64_t* launches)
+static cudaError_t launch_hc_warps(const BatchArgs& a, void* scratch, int variant, int warps_per_sm, uint32_t* counter, const uint32_t* pick,
+                                   const DeviceInfo& dev, cudaStream_t stream, int64_t* launches)
 {
-    if (a.n_blocks <= 0) return cudaSuccess;
     const int warps = hcw_warps(variant, warps_per_sm);
     const int grid = hcw_grid(a.n_blocks, variant, warps_per_sm, dev);
-    cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), stream);
-    if (e != cudaSuccess) return e;
+    cudaError_t e = cudaSuccess;
     if (variant == 1) {
         // residency: the CTA needs HCW_SMEM_BYTES; asking for a larger share of the SM keeps the others out
         int dyn = HCW_SMEM_BYTES;
         if (warps < 3) { const int share = dev.smem_per_sm / warps - 2048; if (share > dyn) dyn = share < dev.smem_optin ? share : dev.smem_optin; }
         e = cudaFuncSetAttribute(lz4_encode_hcw_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
         if (e != cudaSuccess) return e;
-        lz4_encode_hcw_kernel<true, 3><<<(unsigned)grid, 32, dyn, stream>>>(a, (uint8_t*)scratch, counter);
+        lz4_encode_hcw_kernel<true, 3><<<(unsigned)grid, 32, dyn, stream>>>(a, (uint8_t*)scratch, counter, pick);
     } else {
         // all of the SM's on-chip memory as L1 (the blocks' bytes are re-read at random).  Residency below 32 CTAs per SM
         // is a matter of the grid alone: CTAs are placed breadth-first over the SMs and the kernel is persistent.
         if (warps <= 16) {
             e = cudaFuncSetAttribute(lz4_encode_hcw_kernel<false, 16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
             if (e != cudaSuccess) return e;
-            lz4_encode_hcw_kernel<false, 16><<<(unsigned)grid, 32, 0, stream>>>(a, (uint8_t*)scratch, counter);
+            lz4_encode_hcw_kernel<false, 16><<<(unsigned)grid, 32, 0, stream>>>(a, (uint8_t*)scratch, counter, pick);
         } else {
             e = cudaFuncSetAttribute(lz4_encode_hcw_kernel<false, 32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
             if (e != cudaSuccess) return e;
-            lz4_encode_hcw_kernel<false, 32><<<(unsigned)grid, 32, 0, stream>>>(a, (uint8_t*)scratch, counter);
+            lz4_encode_hcw_kernel<false, 32><<<(unsigned)grid, 32, 0, stream>>>(a, (uint8_t*)scratch, counter, pick);
         }
     }
     if (launches) ++*launches;
@@ -196,6 +248,44 @@ cudaError_t launch_encode_hcw(const BatchArgs& a, void* scratch, int variant, in
     lz4_encode_hc_marked_kernel<<<(unsigned)((back + HC_THREADS - 1) / HC_THREADS), HC_THREADS, 0, stream>>>(a, (uint8_t*)scratch);
     if (launches) ++*launches;
     return cudaGetLastError();
+}
+
+cudaError_t launch_encode_hcw(const BatchArgs& a, void* scratch, int variant, int warps_per_sm, uint32_t* counter,
+                              const DeviceInfo& dev, cudaStream_t stream, int64_t* launches)
+{
+    if (a.n_blocks <= 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), stream);
+    if (e != cudaSuccess) return e;
+    return launch_hc_warps(a, scratch, variant, warps_per_sm, counter, nullptr, dev, stream, launches);
+}
+
+// ---- HC, kernel chosen per batch -------------------------------------------------------------------------------------
+// Small batches (at most three blocks per SM): the shared-memory warp kernel, whose time per block is the shortest by far
+// (milliseconds; a lone thread of the thread kernel needs seconds for a block of text).  Larger batches: the pick kernel
+// looks at a sample, then both candidates are enqueued and the one not chosen returns at once.
+bool hc_auto_small(int32_t n_blocks, const DeviceInfo& dev) { return n_blocks <= 3 * dev.num_sms; }
+
+size_t hc_auto_scratch_bytes(int32_t n_blocks, int concurrency, const DeviceInfo& dev)
+{
+    if (hc_auto_small(n_blocks, dev)) return hcw_scratch_bytes(n_blocks, 1, 0, dev);
+    const size_t a = hc_scratch_bytes(concurrency), b = hcw_scratch_bytes(n_blocks, 2, 32, dev);
+    return a > b ? a : b;
+}
+
+cudaError_t launch_encode_hc_auto(const BatchArgs& a, void* scratch, int concurrency, uint32_t* counter /* four words */,
+                                  const DeviceInfo& dev, cudaStream_t stream, int64_t* launches)
+{
+    if (a.n_blocks <= 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(counter, 0, 4 * sizeof(uint32_t), stream);
+    if (e != cudaSuccess) return e;
+    if (hc_auto_small(a.n_blocks, dev)) return launch_hc_warps(a, scratch, 1, 0, counter, nullptr, dev, stream, launches);
+    e = cudaFuncSetAttribute(lz4_hc_pick_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+    if (e != cudaSuccess) return e;
+    lz4_hc_pick_kernel<<<a.n_blocks < HC_PICK_SAMPLE ? a.n_blocks : HC_PICK_SAMPLE, 256, 65536, stream>>>(a, counter);
+    if (launches) ++*launches;
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if ((e = launch_hc_threads(a, scratch, concurrency, counter, counter + 1, stream, launches)) != cudaSuccess) return e;
+    return launch_hc_warps(a, scratch, 2, 32, counter, counter + 1, dev, stream, launches);
 }
 
 }  // namespace lz4b200

@@ -30,6 +30,11 @@ cudaError_t launch_encode_hc(const BatchArgs& a, void* scratch, int concurrency,
 size_t      hcw_scratch_bytes(int32_t n_blocks, int variant, int warps_per_sm, const DeviceInfo& dev);
 cudaError_t launch_encode_hcw(const BatchArgs& a, void* scratch, int variant, int warps_per_sm, uint32_t* counter,
                               const DeviceInfo& dev, cudaStream_t stream, int64_t* launches);
+// kernel chosen per batch: small batches -> the shared-memory warp kernel; large ones -> a sample of the batch decides on
+// the device between the thread kernel and the warp kernel (`counter` = four words)
+size_t      hc_auto_scratch_bytes(int32_t n_blocks, int concurrency, const DeviceInfo& dev);
+cudaError_t launch_encode_hc_auto(const BatchArgs& a, void* scratch, int concurrency, uint32_t* counter,
+                                  const DeviceInfo& dev, cudaStream_t stream, int64_t* launches);
 cudaError_t launch_compact(const uint8_t* slots, const int64_t* slot_off, const int32_t* len, uint8_t* packed,
                            int64_t* out_off, int32_t n_blocks, void* scan_tmp, size_t scan_tmp_bytes,
                            const DeviceInfo& dev, cudaStream_t stream, int64_t* launches);

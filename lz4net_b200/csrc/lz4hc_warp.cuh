@@ -75,6 +75,11 @@ struct Hcw {
         const uint32_t o = SMEM ? simt::atoms_add(sm, (h >> 1) * 4u, inc) : simt::atomg_add(cnt + (h >> 1), inc);
         return (o >> ((h & 1u) * 16u)) & 0xFFFFu;
     }
+    SIMT_MEM uint32_t cnt_add_n(uint32_t h, uint32_t n) const          // += n (global counters), returns the old counter
+    {
+        const uint32_t o = simt::atomg_add(cnt + (h >> 1), (h & 1u) ? (n << 16) : n);
+        return (o >> ((h & 1u) * 16u)) & 0xFFFFu;
+    }
     SIMT_MEM uint32_t cnt_get(uint32_t h) const
     {
         if (SMEM) return simt::lds_u16(sm, h * 2u);
@@ -181,9 +186,7 @@ SIMT_DEV void hcw_build(const Hcw<SMEM>& w)
         carry += simt::shfl(HCW_FULL, x, 31);
     }
     simt::syncwarp(HCW_FULL);
-    // stable scatter, 32 consecutive positions per step (eight steps' hashes requested together).  Lanes that share a hash
-    // inside one step get their indices from the atomic in no particular order: such a step (one lane sees a counter that
-    // is not the value every lane read before) re-ranks the sharing lanes by position.
+    // stable scatter, 32 consecutive positions per step (eight steps' hashes requested together)
     for (int base8 = 1; base8 < P; base8 += 256) {
         uint32_t hh[8];
 #pragma unroll
@@ -195,16 +198,31 @@ SIMT_DEV void hcw_build(const Hcw<SMEM>& w)
             const int p = base + lane;
             const bool act = p < P;
             const uint32_t h = hh[j];
-            const uint32_t c0 = act ? w.cnt_get(h) : 0u;
-            simt::syncwarp(HCW_FULL);
-            uint32_t idx = c0;
-            if (act) idx = w.cnt_add(h);
-            uint32_t pend = simt::ballot(HCW_FULL, act && idx != c0);
-            while (pend) {
-                const uint32_t hl = simt::shfl(HCW_FULL, h, simt::ffs(pend) - 1);
-                const uint32_t same = simt::ballot(HCW_FULL, h == hl);
-                if (h == hl) idx = c0 + (uint32_t)simt::popc(same & ((1u << lane) - 1u));
-                pend &= ~same;
+            uint32_t idx;
+            if (SMEM) {
+                // counters at LDS / ATOMS latency: every lane adds for itself; lanes that share a hash inside the step get
+                // their indices from the atomic in no particular order, so such a step (one lane sees a counter that is not
+                // the value every lane read before) re-ranks the sharing lanes by position
+                const uint32_t c0 = act ? w.cnt_get(h) : 0u;
+                simt::syncwarp(HCW_FULL);
+                idx = c0;
+                if (act) idx = w.cnt_add(h);
+                uint32_t pend = simt::ballot(HCW_FULL, act && idx != c0);
+                while (pend) {
+                    const uint32_t hl = simt::shfl(HCW_FULL, h, simt::ffs(pend) - 1);
+                    const uint32_t same = simt::ballot(HCW_FULL, h == hl);
+                    if (h == hl) idx = c0 + (uint32_t)simt::popc(same & ((1u << lane) - 1u));
+                    pend &= ~same;
+                }
+            } else {
+                // counters an L2 round trip away: the lanes that share a hash are found first (MATCH.ANY is cheaper than a
+                // second round trip), the lowest of them adds the group's size, the others take their place behind it
+                const uint32_t same = simt::match_any(HCW_FULL, h);
+                const int leader = simt::ffs(same) - 1;
+                uint32_t first = 0;
+                if (act && lane == leader) first = w.cnt_add_n(h, (uint32_t)simt::popc(same));
+                first = simt::shfl(HCW_FULL, first, leader);
+                idx = first + (uint32_t)simt::popc(same & ((1u << lane) - 1u));
             }
             if (act) { simt::stg_u16(w.sorted + idx, (uint32_t)p); simt::stg_u16(w.rank + p, idx); }
             simt::syncwarp(HCW_FULL);

@@ -22,10 +22,11 @@ def ctx():
     return lz4net_b200.default_context()
 
 
-@pytest.fixture(params=[0, 1, 2], ids=["hc-thread", "hc-warp-smem", "hc-warp-l1"])
+@pytest.fixture(params=[-1, 0, 1, 2], ids=["hc-auto", "hc-thread", "hc-warp-smem", "hc-warp-l1"])
 def hck(ctx, request):
     """Every HC kernel of the library (lz4hc_encode.cuh: a thread per block; lz4hc_warp.cuh: a warp per block on a static
-    index, block staged in shared memory / read through L1) emits the reference's bytes."""
+    index, block staged in shared memory / read through L1) emits the reference's bytes, and so does the default, which
+    chooses per batch."""
     prev = ctx.get_option("hc_kernel")
     ctx.set_option("hc_kernel", request.param)
     yield request.param
@@ -290,6 +291,28 @@ def test_device_batch_hc_sampled_parity(ctx, hck):
     for i in range(0, nb, 61):
         r, o = oracle.encode_hc(h_raw[i])
         assert h_len[i] == r and h_slots[i, :r].tobytes() == o, i
+
+
+@pytest.mark.parametrize("cid,name", [(1, "E50"), (3, "ETEXT")])
+def test_hc_kernel_chosen_on_the_device(ctx, cid, name):
+    """Batches of more than three blocks per SM: a sample of the batch decides on the device between the thread kernel
+    (shallow hash buckets: E50) and the warp kernel (deep ones: ETEXT); whichever runs, the bytes are the reference's."""
+    import torch
+    from lz4net_b200 import batch
+    assert ctx.get_option("hc_kernel") == -1
+    nb, bs = 600, 65536
+    slot = oracle.bound(bs)
+    raw = torch.empty(nb * bs, dtype=torch.uint8, device="cuda")
+    batch.synth_fill(ctx, raw, nb, bs, cid, seed=9, first_block=0)
+    so, do, sl, dc = batch.uniform_layout(nb, bs, slot, "cuda")
+    slots = torch.empty(nb * slot, dtype=torch.uint8, device="cuda")
+    clen = torch.zeros(nb, dtype=torch.int32, device="cuda")
+    batch.encode(ctx, raw, so, sl, slots, do, dc, clen, hc=True)
+    torch.cuda.synchronize()
+    h_raw = raw.cpu().numpy().reshape(nb, bs); h_len = clen.cpu().numpy(); h_slots = slots.cpu().numpy().reshape(nb, slot)
+    for i in list(range(0, nb, 37)) + [nb - 1]:
+        r, o = oracle.encode_hc(h_raw[i])
+        assert h_len[i] == r and h_slots[i, :r].tobytes() == o, (name, i)
 
 
 def test_single_block_entry_points_and_autotest(ctx):

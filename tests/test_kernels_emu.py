@@ -289,10 +289,10 @@ def test_encode_hcw_matches_oracle(model):
     """Byte-identical to LZ4_compressHC_limitedOutput (original/lz4hc.c:745-755): the chain walks of :423-433 / :477-514
     replaced by gathers from the sorted hash buckets."""
     done = 0
-    for i, n in enumerate([65536, 65535, 4097] + cases.random_lengths(4, 65536, seed=5)):
+    for i, n in enumerate([65536, 65535, 4097] + cases.random_lengths(2, 65536, seed=5)):
         d = cases.content(model, n, seed=500 + i).tobytes()
         done += _hcw_check(d, sched_seed=3 + i)
-    assert done >= 6, "the static index should describe (nearly) every block"
+    assert done >= 4, "the static index should describe (nearly) every block"
 
 
 def test_encode_hcw_boundary_lengths():
@@ -308,7 +308,7 @@ def test_encode_hcw_limited_output_and_alignment():
         r, _ = oracle.encode_hc(d)
         for cap in (r, r - 1, len(d), len(d) - 1, r // 2, 0, 1, 7, 8, 13):
             assert _hcw_check(d, cap=cap), (m, cap)
-        for skew in range(1, 16):
+        for skew in (1, 2, 3, 5, 8, 13, 15):
             assert _hcw_check(d, src_skew=skew, dst_skew=(skew * 5) % 16, sched_seed=skew), (m, skew)
     # the capacity swept over a whole compressed block: every limit check of :529 / :541 / :731 fails once
     d = cases.content("ETEXT", 1200, seed=5).tobytes()
