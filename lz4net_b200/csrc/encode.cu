@@ -229,17 +229,12 @@ static cudaError_t launch_hc_warps(const BatchArgs& a, void* scratch, int varian
         if (e != cudaSuccess) return e;
         lz4_encode_hcw_kernel<true, 3><<<(unsigned)grid, 32, dyn, stream>>>(a, (uint8_t*)scratch, counter, pick);
     } else {
-        // all of the SM's on-chip memory as L1 (the blocks' bytes are re-read at random).  Residency below 32 CTAs per SM
-        // is a matter of the grid alone: CTAs are placed breadth-first over the SMs and the kernel is persistent.
-        if (warps <= 16) {
-            e = cudaFuncSetAttribute(lz4_encode_hcw_kernel<false, 16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
-            if (e != cudaSuccess) return e;
-            lz4_encode_hcw_kernel<false, 16><<<(unsigned)grid, 32, 0, stream>>>(a, (uint8_t*)scratch, counter, pick);
-        } else {
-            e = cudaFuncSetAttribute(lz4_encode_hcw_kernel<false, 32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
-            if (e != cudaSuccess) return e;
-            lz4_encode_hcw_kernel<false, 32><<<(unsigned)grid, 32, 0, stream>>>(a, (uint8_t*)scratch, counter, pick);
-        }
+        // Residency below 32 CTAs per SM is a matter of the grid alone: CTAs are placed breadth-first over the SMs and the
+        // kernel is persistent.  No shared-memory carve-out preference: asking for "all L1" (cudaSharedmemCarveoutMaxL1)
+        // left room for the system-reserved KiB of only a handful of CTAs per SM -- 16 to 32 warps per SM all ran at the
+        // speed of 8 (profiles/hc_ab_r02d.json: identical times); the default lets the driver size it for the occupancy.
+        if (warps <= 16) lz4_encode_hcw_kernel<false, 16><<<(unsigned)grid, 32, 0, stream>>>(a, (uint8_t*)scratch, counter, pick);
+        else             lz4_encode_hcw_kernel<false, 32><<<(unsigned)grid, 32, 0, stream>>>(a, (uint8_t*)scratch, counter, pick);
     }
     if (launches) ++*launches;
     e = cudaGetLastError();

@@ -20,6 +20,10 @@ budget = float(sys.argv[1]) if len(sys.argv) > 1 else 200.0          # seconds t
 ctx = lz4net_b200.Context(0)
 out = {"device": torch.cuda.get_device_name(0), "block": BLOCK, "runs": []}
 CONFIGS = [(0, 0), (-1, 0), (2, 32), (2, 24), (1, 3), (2, 16), (2, 28), (2, 20)]
+if len(sys.argv) > 2:                                                  # e.g. "2:32,2:24,-1:0": a chosen subset (no kernel 0: no byte comparison)
+    CONFIGS = [tuple(int(x) for x in c.split(":")) for c in sys.argv[2].split(",")]
+CLASSES = (("E50", 65536), ("ETEXT", 32768), ("TEXT", 16384))
+LONE = len(sys.argv) <= 2
 
 
 def timed(w, kernel, warps):
@@ -46,7 +50,7 @@ def text_blocks(nb):
     return t.repeat((nb + k - 1) // k, 1)[:nb].contiguous().view(-1), k
 
 
-for cls, nb in (("E50", 65536), ("ETEXT", 32768), ("TEXT", 16384)):
+for cls, nb in CLASSES:
     w = Workload(ctx, nb, "E0" if cls == "TEXT" else cls, nb, seed=3)
     if cls == "TEXT":
         w.raw, distinct = text_blocks(nb)
@@ -62,7 +66,7 @@ for cls, nb in (("E50", 65536), ("ETEXT", 32768), ("TEXT", 16384)):
         bytes_ = [slots[i, : int(lens[i])].clone() for i in sample]
         if kernel == 0:
             ref_len, ref_bytes = lens, bytes_
-        same = bool(torch.equal(lens, ref_len)) and all(torch.equal(a, b) for a, b in zip(bytes_, ref_bytes))
+        same = None if ref_len is None else bool(torch.equal(lens, ref_len)) and all(torch.equal(a, b) for a, b in zip(bytes_, ref_bytes))
         row = {"class": cls, "blocks": nb, "hc_kernel": kernel, "warps_per_sm": warps, "seconds": round(t, 4),
                "gbs": round(nb * BLOCK / t / GB, 2), "ratio": round(int(lens.sum()) / (nb * BLOCK), 4), "same_as_kernel0": same}
         out["runs"].append(row)
@@ -77,7 +81,7 @@ for cls, nb in (("E50", 65536), ("ETEXT", 32768), ("TEXT", 16384)):
 
 # latency of a lone block (the single-block EncodeHC entry point's case): host timed, one block per call
 w = Workload(ctx, 1, "ETEXT", 1, seed=3)
-for kernel in (-1, 0):
+for kernel in ((-1, 0) if LONE else ()):
     ctx.set_option("hc_kernel", kernel); ctx.set_option("hc_warps_per_sm", 0)
     w.encode(hc=True); torch.cuda.synchronize()
     t0 = time.time(); w.encode(hc=True); torch.cuda.synchronize(); dt = time.time() - t0
