@@ -137,13 +137,18 @@ lz4_encode_hcw_kernel(BatchArgs a, uint8_t* arena, uint32_t* counter, const uint
     }
 }
 
-// Auto mode, large batches: which kernel pays is a property of the data -- the index pays when chain walks are long.
-// A sample of the batch (up to 32 blocks, evenly spaced; one CTA each) is hashed into 15-bit buckets in shared memory;
-// depth = sum(min(c, 255) * c) / sum(c) over the buckets = the (clamped) bucket size an average position sees.
+// Auto mode, large batches: a sample of the batch (up to 32 blocks, evenly spaced; one CTA each) is looked at on the device.
+// What decides today is the block size alone -- the warp kernel takes blocks of at most 64 KiB and hands the others to a
+// few thousand threads, so a batch made mostly of larger blocks goes to the thread kernel.  The sample's hash-bucket
+// statistic (depth = sum(min(c, 255) * c) / sum(c) = the clamped bucket size an average position sees: E0 3.0, E50 3.9,
+// natural text and code 20 - 66, ETEXT 240) is computed as well: with the warp kernel capped at 8 resident warps per SM by a
+// shared-memory carve-out preference it separated the batches the index paid for (depth >= 8) from those it did not; at its
+// real residency the warp kernel is ahead on every class measured (profiles/hc_ab_r02e.json: E50 10.5 against 9.7), so the
+// threshold is 0 and the statistic is kept for the record only.
 // words: [0] block counter of the codec kernels (used as the ticket here and left zero), [1] pick (0 thread kernel,
-// 2 warp kernel), [2] sum(c), [3] sum(min(c,255)*c).
+// 2 warp kernel), [2] sum(c), [3] sum(min(c,255)*c) / 16.
 constexpr int HC_PICK_SAMPLE = 32;
-constexpr uint32_t HC_PICK_DEPTH_X16 = 8 * 16;             // warp kernel from an average bucket size of 8
+constexpr uint32_t HC_PICK_DEPTH_X16 = 0;                  // warp kernel from this average bucket size (x16) on: always
 
 __global__ void __launch_bounds__(256)
 lz4_hc_pick_kernel(BatchArgs a, uint32_t* words)
@@ -198,7 +203,7 @@ lz4_encode_hc_marked_kernel(BatchArgs a, uint8_t* arena)
 
 constexpr int HCW_FALLBACK_THREADS = 4096;                 // thread-per-block slots kept for handed-back blocks (1 GiB of state)
 
-static int hcw_warps(int variant, int warps_per_sm) { const int mx = variant == 1 ? 3 : 32; return warps_per_sm < 1 || warps_per_sm > mx ? (variant == 1 ? 3 : 16) : warps_per_sm; }
+static int hcw_warps(int variant, int warps_per_sm) { const int mx = variant == 1 ? 3 : 32; return warps_per_sm < 1 || warps_per_sm > mx ? mx : warps_per_sm; }
 
 static int hcw_grid(int32_t n_blocks, int variant, int warps_per_sm, const DeviceInfo& dev)
 {
@@ -256,8 +261,8 @@ cudaError_t launch_encode_hcw(const BatchArgs& a, void* scratch, int variant, in
 
 // ---- HC, kernel chosen per batch -------------------------------------------------------------------------------------
 // Small batches (at most three blocks per SM): the shared-memory warp kernel, whose time per block is the shortest by far
-// (milliseconds; a lone thread of the thread kernel needs seconds for a block of text).  Larger batches: the pick kernel
-// looks at a sample, then both candidates are enqueued and the one not chosen returns at once.
+// (20 ms for a lone block of text; a lone thread of the thread kernel needs 0.23 s, and seconds inside a full batch).
+// Larger batches: the pick kernel looks at a sample, then both candidates are enqueued and the one not chosen returns at once.
 bool hc_auto_small(int32_t n_blocks, const DeviceInfo& dev) { return n_blocks <= 3 * dev.num_sms; }
 
 size_t hc_auto_scratch_bytes(int32_t n_blocks, int concurrency, const DeviceInfo& dev)

@@ -295,8 +295,9 @@ def test_device_batch_hc_sampled_parity(ctx, hck):
 
 @pytest.mark.parametrize("cid,name", [(1, "E50"), (3, "ETEXT")])
 def test_hc_kernel_chosen_on_the_device(ctx, cid, name):
-    """Batches of more than three blocks per SM: a sample of the batch decides on the device between the thread kernel
-    (shallow hash buckets: E50) and the warp kernel (deep ones: ETEXT); whichever runs, the bytes are the reference's."""
+    """Batches of more than three blocks per SM: a sample of the batch is looked at on the device (block sizes, hash-bucket
+    depth), the thread kernel and the warp kernel are both enqueued and one of them runs; whichever does, the bytes are the
+    reference's."""
     import torch
     from lz4net_b200 import batch
     assert ctx.get_option("hc_kernel") == -1
@@ -313,6 +314,28 @@ def test_hc_kernel_chosen_on_the_device(ctx, cid, name):
     for i in list(range(0, nb, 37)) + [nb - 1]:
         r, o = oracle.encode_hc(h_raw[i])
         assert h_len[i] == r and h_slots[i, :r].tobytes() == o, (name, i)
+
+
+def test_hc_large_batch_of_blocks_above_64k(ctx):
+    """The same choice with a batch made of blocks the warp kernel cannot take (128 KiB): thread kernel; and with a minority
+    of them among 64 KiB blocks: warp kernel, the large blocks handed back inside the call."""
+    import torch
+    from lz4net_b200 import batch
+    for nb, bs, lens in ((500, 131072, None), (640, 131072, 65536)):
+        slot = oracle.bound(bs)
+        raw = torch.empty(nb * bs, dtype=torch.uint8, device="cuda")
+        batch.synth_fill(ctx, raw, nb * (bs // 65536), 65536, 3, seed=4, first_block=0)
+        so, do, sl, dc = batch.uniform_layout(nb, bs, slot, "cuda")
+        if lens is not None:                      # three of four blocks use only the first 64 KiB of their slot
+            sl = sl.clone(); sl[torch.arange(nb, device="cuda") % 4 != 0] = lens
+        slots = torch.empty(nb * slot, dtype=torch.uint8, device="cuda")
+        clen = torch.zeros(nb, dtype=torch.int32, device="cuda")
+        batch.encode(ctx, raw, so, sl, slots, do, dc, clen, hc=True)
+        torch.cuda.synchronize()
+        h_raw = raw.cpu().numpy().reshape(nb, bs); h_len = clen.cpu().numpy(); h_slots = slots.cpu().numpy().reshape(nb, slot); h_sl = sl.cpu().numpy()
+        for i in list(range(0, nb, 41)) + [nb - 1, nb - 2]:
+            r, o = oracle.encode_hc(h_raw[i, :h_sl[i]])
+            assert h_len[i] == r and h_slots[i, :r].tobytes() == o, (nb, i)
 
 
 def test_single_block_entry_points_and_autotest(ctx):
