@@ -154,7 +154,8 @@ int run_device(lz4b200_ctx* c, const BatchArgs& a, int op /*0 enc fast, 1 enc hc
     switch (op) {
     case 0: e = launch_encode_fast(a, c->counter(), c->encode_ctas_per_sm, c->encode_tune, c->encode_variant, c->dev, st, &c->launches); break;
     case 1: {
-        const int conc = (int)std::min<int64_t>(c->hc_concurrency, std::max(a.n_blocks, 1));
+        // (chosen per batch: the thread kernel only runs for batches of blocks above 64 KiB -- 4 GiB of state at most there)
+        const int conc = (int)std::min<int64_t>(c->hc_kernel < 0 ? std::min(c->hc_concurrency, 16384) : c->hc_concurrency, std::max(a.n_blocks, 1));
         const size_t need = c->hc_kernel < 0 ? hc_auto_scratch_bytes(a.n_blocks, conc, c->dev)
                           : (c->hc_kernel ? hcw_scratch_bytes(a.n_blocks, c->hc_kernel, c->hc_warps_per_sm, c->dev) : hc_scratch_bytes(conc));
         if (need > c->hc_arena.cap) {
