@@ -11,8 +11,8 @@
 //     the positions < q of q's hash bucket in descending order, then position 0, then stops
 // (chain[0] = 0xFFFF leads below ip - 65535; no delta is clamped and no slot aliases in 64 KiB).  So the warp
 //   1. BUILDS the index once per block: a stable counting sort of the positions by hash (`sorted`, bucket by bucket in
-//      ascending position) and each position's place in it (`rank`) -- histogram and stable scatter with shared-memory
-//      atomics, 32 positions per step;
+//      ascending position) and each position's place in it (`rank`) -- histogram and stable scatter with atomics on
+//      packed u16 counters (in shared memory, or in the warp's arena slot), 32 positions per step;
 //   2. searches by GATHER: the candidates of q are sorted[rank[q]-1], sorted[rank[q]-2], ... -- consecutive entries, one
 //      coalesced load for 32 of them, scored by the 32 lanes at once (common length / backward extension per lane, the
 //      reference's "first candidate that beats everything before it" = first maximum, one REDUX);
