@@ -363,3 +363,18 @@ def test_encode_hcw_hands_back_what_the_static_index_does_not_describe():
     assert emu.encode_hcw(d)[0] == emu.HCW_FALLBACK
     # the same run with a triple that does not collide is encoded here
     assert _hcw_check(rng.integers(0, 256, 500, dtype=np.uint8).tobytes() + bytes([1, 2, 3]) * 200 + bytes(500))
+
+
+def test_encode_hc_gives_up_at_the_bound_like_the_reference():
+    """r93's LZ4HC can return 0 with a destination of LZ4_compressBound(n) bytes: incompressible data with one late match
+    (about one random 64 KiB block in 400).  The reference compiled in place, the port and every kernel agree on it."""
+    from lz4net_b200 import synth
+    d = synth.make_blocks("E0", 1, 65536, seed=3, first_block=1268)[0].tobytes()
+    cap = oracle.bound(len(d))
+    assert oracle.encode_hc(d, cap=cap)[0] == 0 and oracle.encode_hc(d, cap=cap + 4096)[0] == 65794
+    if oracle.have_ref():
+        assert oracle.encode_hc(d, cap=cap, impl="ref")[0] == 0
+    assert emu.encode_hc(d, cap=cap)[0] == 0
+    for smem in (True, False):
+        assert emu.encode_hcw(d, cap=cap, smem=smem)[0] == 0
+        assert emu.encode_hcw(d, cap=cap + 4096, smem=smem) == oracle.encode_hc(d, cap=cap + 4096)
