@@ -16,3 +16,5 @@ SMALL="--blocks 151552 --steps 2 --warmup 1 --no-sweep --no-hc --no-cpu --no-e2e
 echo "=== ncu launch list ==="
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py $SMALL > gpurun_out/ncu_launch_$TAG.log 2>&1
 grep -c lz4 gpurun_out/launches_$TAG.csv
+echo "=== LZ4HC kernels side by side ==="
+timeout 300 python tools/hc_ab.py 200 2>&1 | tail -40 | tee gpurun_out/hc_ab_$TAG.txt
